@@ -1,0 +1,99 @@
+/* libb200gp -- C ABI of the B200-native candidate-kernel scoring path.
+ *
+ * Drop-in boundary for the arithmetic the reference (lschlessinger1/MS-project, src/autoks) delegates to
+ * GPy / NumPy-LAPACK when it scores a candidate kernel:
+ *   GPModel.score_model / fit              src/autoks/core/gp_model.py:31-82
+ *     -> GPy GP.parameters_changed / ExactGaussianInference.inference (K, jitchol, pdinv, dpotrs, gradients)
+ *   compute_kernel                         src/autoks/backend/kernel.py:317-322
+ *   HellingerDistanceBuilder               src/autoks/distance/distance.py:126-194
+ *
+ * Conventions
+ *   - one opaque context per GPU; a context is not thread-safe, distinct contexts are independent;
+ *   - every pointer marked `d_` is a CALLER-OWNED DEVICE pointer (e.g. torch tensor.data_ptr()), FP64 / int32,
+ *     row-major; the library allocates no device memory of its own: the caller hands it one workspace;
+ *   - every function returns 0 on success, <0 on API misuse or a CUDA error (text in b200gp_last_error);
+ *     NUMERICAL failures are per-item status codes, never a non-zero return;
+ *   - all work is enqueued on the context's stream; functions that must read device results on the host
+ *     (jitter ladder) synchronise that stream, the others return asynchronously.
+ *
+ * Kernel programs (compiled on the host from Covariance.postfix_tokens, src/autoks/core/covariance.py:32-45):
+ *   int32 quadruples {op, a, b, 0}:  leaf   {B200GP_OP_SE..CONST, active_dim (0-based), theta offset, 0}
+ *                                    binary {B200GP_OP_ADD|MUL, lhs token index, rhs token index, 0}
+ *   in postfix order; the last token is the root.  prog_off[M+1] counts tokens.
+ *   theta is the GPy param_array of each item's kernel followed by Gaussian_noise.variance (constrained
+ *   values, i.e. after the Logexp transform); theta_off[M+1] counts doubles (P_i + 1 per item).
+ *   Leaf parameter order: SE [variance, lengthscale]; RQ [variance, lengthscale, power];
+ *   PER [variance, period, lengthscale]; LIN [variances, shifts]; CONST [variance].
+ */
+#ifndef B200GP_H
+#define B200GP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200gp_ctx b200gp_ctx;
+
+enum { B200GP_OP_SE = 0, B200GP_OP_RQ = 1, B200GP_OP_PER = 2, B200GP_OP_LIN = 3, B200GP_OP_CONST = 4,
+       B200GP_OP_ADD = 5, B200GP_OP_MUL = 6 };
+
+/* per-item status */
+enum { B200GP_OK = 0, B200GP_JITTERED = 1, B200GP_NOT_PD = 2, B200GP_NONFINITE = 3 };
+
+/* gradient quirk bits: reproduce the fork's notebook formulas instead of the exact derivative */
+enum { B200GP_QUIRK_PER_LENGTHSCALE = 1, B200GP_QUIRK_LIN_SHIFT = 2 };
+
+enum { B200GP_TILE = 128, B200GP_MAX_DIMS = 16, B200GP_MAX_TOKENS = 64, B200GP_MAX_PARAMS = 128 };
+
+const char* b200gp_version(void);
+
+/* context on `device`, enqueueing on `cuda_stream` (a cudaStream_t; NULL = legacy default stream) */
+int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out);
+int b200gp_destroy(b200gp_ctx* ctx);
+const char* b200gp_last_error(b200gp_ctx* ctx);
+int b200gp_set_quirks(b200gp_ctx* ctx, int quirk_mask);
+
+/* Workspace needed to score `slots` matrices of order N at a time (bytes). */
+size_t b200gp_workspace_bytes(int N, int D, int slots, int max_params);
+
+/* Bind the training data and the workspace.  d_X is N x D row-major, d_y has N entries (GPy's Y is N x 1;
+ * ModelSelector._prepare_data standardises both, base.py:200-222).  The library keeps padded,
+ * dimension-major copies inside the workspace. */
+int b200gp_bind(b200gp_ctx* ctx, void* d_workspace, size_t workspace_bytes, int slots, int max_params,
+                const double* d_X, int N, int D, const double* d_y);
+
+/* kern.K(X) for the n items ids[0..n) over the bound X: d_K_out is n x N x N (symmetric, dense).
+ * add_diag = 0: the bare kernel matrix (compute_kernel, backend/kernel.py:317-322);
+ * add_diag = 1: K_y = K + (noise + 1e-8) I as ExactGaussianInference forms it. */
+int b200gp_build_K(b200gp_ctx* ctx, const int32_t* d_prog, const int32_t* d_prog_off, const double* d_theta,
+                   const int32_t* d_theta_off, const int32_t* d_ids, int n, int add_diag, double* d_K_out);
+
+/* Log marginal likelihood and its gradient w.r.t. the constrained parameters [theta_kernel..., noise]
+ * for the n items ids[0..n) (GP.log_likelihood() and the `.gradient` fields GP.parameters_changed fills).
+ * Outputs are indexed by ITEM id: d_lml[item], d_dlml[theta_off[item] ...], d_status[item],
+ * d_tries[item] (jitter-ladder tries, 0 = plain factorisation; may be NULL).
+ * with_grad = 0 skips K^-1 and the gradient pass.  Synchronises the stream. */
+int b200gp_lml_grad(b200gp_ctx* ctx, const int32_t* d_prog, const int32_t* d_prog_off, const double* d_theta,
+                    const int32_t* d_theta_off, const int32_t* d_ids, int n, int with_grad, double* d_lml,
+                    double* d_dlml, int32_t* d_status, int32_t* d_tries);
+
+/* In-place blocked Cholesky of ONE dense SPD matrix (lower triangle; N a multiple of 128), the
+ * `dpotrf` of GPy's jitchol at large N.  d_work needs b200gp_potrf_work_bytes(N) bytes.
+ * logdet / status are HOST outputs (status 0 ok, >0 = 1-based index of the first bad pivot). */
+size_t b200gp_potrf_work_bytes(int N);
+int b200gp_potrf(b200gp_ctx* ctx, double* d_A, int N, void* d_work, double* logdet, int32_t* status);
+
+/* Phase timings (ms) of the most recent b200gp_lml_grad chunk, measured with CUDA events on the context
+ * stream: [build_K, cholesky, inverse(V), solve, Kinv, grad+finalize].  Returns the number written. */
+int b200gp_last_phase_ms(b200gp_ctx* ctx, float* out, int cap);
+int b200gp_set_profiling(b200gp_ctx* ctx, int enabled);
+/* kernels launched by this context since creation (for bench.py's gpu_launches) */
+long long b200gp_launch_count(b200gp_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GP_H */

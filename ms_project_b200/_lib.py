@@ -1,0 +1,101 @@
+"""ctypes binding of libb200gp.so (include/b200gp.h).  There is no CPU fallback: a missing or
+unloadable library is an ImportError-grade failure raised the moment anything needs the device."""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libb200gp.so')
+CSRC = os.path.join(_HERE, 'csrc')
+
+_lib = None
+
+c_int_p = ctypes.POINTER(ctypes.c_int32)
+c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+class B200GPError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile csrc/*.cu for sm_100a into ms_project_b200/libb200gp.so (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(['make', '-C', CSRC, '-j8'], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise B200GPError('building libb200gp.so failed')
+    return LIB_PATH
+
+
+def _declare(lib):
+    vp = ctypes.c_void_p
+    lib.b200gp_version.restype = ctypes.c_char_p
+    lib.b200gp_version.argtypes = []
+    lib.b200gp_create.restype = ctypes.c_int
+    lib.b200gp_create.argtypes = [ctypes.c_int, vp, ctypes.POINTER(vp)]
+    lib.b200gp_destroy.restype = ctypes.c_int
+    lib.b200gp_destroy.argtypes = [vp]
+    lib.b200gp_last_error.restype = ctypes.c_char_p
+    lib.b200gp_last_error.argtypes = [vp]
+    lib.b200gp_set_quirks.restype = ctypes.c_int
+    lib.b200gp_set_quirks.argtypes = [vp, ctypes.c_int]
+    lib.b200gp_set_profiling.restype = ctypes.c_int
+    lib.b200gp_set_profiling.argtypes = [vp, ctypes.c_int]
+    lib.b200gp_launch_count.restype = ctypes.c_longlong
+    lib.b200gp_launch_count.argtypes = [vp]
+    lib.b200gp_last_phase_ms.restype = ctypes.c_int
+    lib.b200gp_last_phase_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+    lib.b200gp_workspace_bytes.restype = ctypes.c_size_t
+    lib.b200gp_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.b200gp_bind.restype = ctypes.c_int
+    lib.b200gp_bind.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.b200gp_build_K.restype = ctypes.c_int
+    lib.b200gp_build_K.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]
+    lib.b200gp_lml_grad.restype = ctypes.c_int
+    lib.b200gp_lml_grad.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    lib.b200gp_potrf_work_bytes.restype = ctypes.c_size_t
+    lib.b200gp_potrf_work_bytes.argtypes = [ctypes.c_int]
+    lib.b200gp_potrf.restype = ctypes.c_int
+    lib.b200gp_potrf.argtypes = [vp, vp, ctypes.c_int, vp, c_double_p, c_int_p]
+    for name, args in _OPTIONAL.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = args
+
+
+_vp = ctypes.c_void_p
+_OPTIONAL = {
+    'b200gp_hellinger_precompute': [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,
+                                    ctypes.c_int, _vp, _vp, _vp],
+    'b200gp_hellinger_pairs': [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int,
+                               ctypes.c_double, _vp, _vp],
+}
+
+EXPORTS = ['b200gp_version', 'b200gp_create', 'b200gp_destroy', 'b200gp_last_error', 'b200gp_set_quirks',
+           'b200gp_set_profiling', 'b200gp_launch_count', 'b200gp_last_phase_ms', 'b200gp_workspace_bytes',
+           'b200gp_bind', 'b200gp_build_K', 'b200gp_lml_grad', 'b200gp_potrf_work_bytes', 'b200gp_potrf']
+
+
+def lib():
+    """The loaded library; raises B200GPError (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200GPError('%s is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                              '(there is no CPU fallback)' % LIB_PATH)
+        try:
+            l = ctypes.CDLL(LIB_PATH)
+        except OSError as e:
+            raise B200GPError('cannot load %s: %s' % (LIB_PATH, e))
+        _declare(l)
+        _lib = l
+    return _lib
+
+
+def check(ctx, rc, what):
+    if rc != 0:
+        msg = lib().b200gp_last_error(ctx)
+        raise B200GPError('%s failed (rc=%d): %s' % (what, rc, msg.decode() if msg else ''))

@@ -1,0 +1,381 @@
+// C-ABI of libb200gp (include/b200gp.h): context, workspace carving, phase orchestration, jitter ladder.
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200gp.h"
+#include "kernels.cuh"
+
+using namespace b200gp;
+
+namespace b200gp {
+long long g_launch_count = 0;
+void launch_pack_data(const double* X, const double* y, int N, int D, int Np, double* Xt, double* yp, cudaStream_t s);
+}
+
+struct b200gp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int quirks = 0;
+  bool bound = false;
+  bool profiling = false;
+  Batch base{};             // geometry + workspace pointers
+  int slots = 0, max_params = 0;
+  double* ws_jitter = nullptr;
+  int* ws_ids = nullptr;
+  int* ws_tries_dummy = nullptr;
+  // pinned host staging
+  int* h_status = nullptr;
+  int* h_ids = nullptr;
+  double* h_diag = nullptr;
+  double* h_jit = nullptr;
+  size_t h_cap = 0;
+  cudaEvent_t ev[8]{};
+  float phase_ms[6]{};
+  int n_phase = 0;
+};
+
+static int fail(b200gp_ctx* c, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return -1;
+}
+#define CUCHECK(c, expr)                                                                     \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) return fail(c, "%s failed: %s", #expr, cudaGetErrorString(_e));  \
+  } while (0)
+
+namespace {
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) / 256 * 256;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct Layout {
+  double *M1, *M2, *Dinv, *z, *alpha, *logdet_part, *diag_part, *grad_part, *Xt, *y, *jitter;
+  int *slot_status, *ids;
+  size_t bytes;
+};
+
+Layout carve(void* ws, int N, int D, int slots, int max_params) {
+  const int Np = round_up(N, NB), T = Np / NB;
+  const size_t S = (size_t)slots;
+  Carver c(ws);
+  Layout l;
+  l.M1 = c.take<double>(S * Np * Np);
+  l.M2 = c.take<double>(S * Np * Np);
+  l.Dinv = c.take<double>(S * T * NB * NB);
+  l.z = c.take<double>(S * Np);
+  l.alpha = c.take<double>(S * Np);
+  l.logdet_part = c.take<double>(S * T);
+  l.diag_part = c.take<double>(S * T);
+  l.grad_part = c.take<double>(S * tri_count(T) * (size_t)(max_params + 1));
+  l.Xt = c.take<double>((size_t)D * Np);
+  l.y = c.take<double>(Np);
+  l.jitter = c.take<double>(S);
+  l.slot_status = c.take<int>(S);
+  l.ids = c.take<int>(S);
+  l.bytes = c.off + 256;
+  return l;
+}
+}  // namespace
+
+extern "C" {
+
+const char* b200gp_version(void) { return "b200gp 0.1 (sm_100a, FP64 DMMA)"; }
+
+int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
+  if (!out) return -1;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return -2;
+  if (cudaSetDevice(device) != cudaSuccess) return -3;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -3;
+  if (prop.major < 10) return -4;   // sm_100a only: there is no fallback path
+  if (configure_kernels() != 0) return -5;
+  b200gp_ctx* c = new b200gp_ctx();
+  c->device = device;
+  c->stream = static_cast<cudaStream_t>(cuda_stream);
+  for (auto& e : c->ev) cudaEventCreate(&e);
+  *out = c;
+  return 0;
+}
+
+int b200gp_destroy(b200gp_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  for (auto& e : c->ev) cudaEventDestroy(e);
+  if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->h_ids) cudaFreeHost(c->h_ids);
+  if (c->h_diag) cudaFreeHost(c->h_diag);
+  if (c->h_jit) cudaFreeHost(c->h_jit);
+  delete c;
+  return 0;
+}
+
+const char* b200gp_last_error(b200gp_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int b200gp_set_quirks(b200gp_ctx* c, int mask) {
+  if (!c) return -1;
+  c->quirks = mask;
+  return 0;
+}
+
+int b200gp_set_profiling(b200gp_ctx* c, int enabled) {
+  if (!c) return -1;
+  c->profiling = enabled != 0;
+  return 0;
+}
+
+long long b200gp_launch_count(b200gp_ctx*) { return g_launch_count; }
+
+int b200gp_last_phase_ms(b200gp_ctx* c, float* out, int cap) {
+  if (!c || !out) return -1;
+  int n = c->n_phase < cap ? c->n_phase : cap;
+  for (int i = 0; i < n; i++) out[i] = c->phase_ms[i];
+  return n;
+}
+
+size_t b200gp_workspace_bytes(int N, int D, int slots, int max_params) {
+  if (N <= 0 || D <= 0 || slots <= 0 || max_params < 0) return 0;
+  return carve(nullptr, N, D, slots, max_params).bytes;
+}
+
+int b200gp_bind(b200gp_ctx* c, void* ws, size_t ws_bytes, int slots, int max_params, const double* dX, int N, int D,
+                const double* dy) {
+  if (!c) return -1;
+  if (!ws || !dX || !dy) return fail(c, "b200gp_bind: null pointer");
+  if (N <= 0 || D <= 0 || D > MAX_DIMS) return fail(c, "b200gp_bind: need 0 < N, 0 < D <= %d", MAX_DIMS);
+  if (slots <= 0) return fail(c, "b200gp_bind: slots must be positive");
+  if (max_params < 1 || max_params > MAX_PARAMS) return fail(c, "b200gp_bind: max_params must be in [1, %d]", MAX_PARAMS);
+  const size_t need = b200gp_workspace_bytes(N, D, slots, max_params);
+  if (ws_bytes < need) return fail(c, "b200gp_bind: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(c, "b200gp_bind: workspace must be 256-byte aligned");
+  CUCHECK(c, cudaSetDevice(c->device));
+  Layout l = carve(ws, N, D, slots, max_params);
+  Batch& b = c->base;
+  b = Batch{};
+  b.N = N; b.Np = round_up(N, NB); b.T = b.Np / NB; b.D = D;
+  b.mstride = (size_t)b.Np * b.Np;
+  b.M1 = l.M1; b.M2 = l.M2; b.Dinv = l.Dinv; b.z = l.z; b.alpha = l.alpha;
+  b.logdet_part = l.logdet_part; b.diag_part = l.diag_part; b.grad_part = l.grad_part;
+  b.pstride = max_params + 1;
+  b.slot_status = l.slot_status;
+  b.Xt = l.Xt; b.y = l.y;
+  c->ws_jitter = l.jitter; c->ws_ids = l.ids;
+  c->slots = slots; c->max_params = max_params;
+  launch_pack_data(dX, dy, N, D, b.Np, l.Xt, l.y, c->stream);
+  CUCHECK(c, cudaGetLastError());
+  const size_t cap = (size_t)slots;
+  if (cap > c->h_cap) {
+    if (c->h_status) { cudaFreeHost(c->h_status); cudaFreeHost(c->h_ids); cudaFreeHost(c->h_diag); cudaFreeHost(c->h_jit); }
+    CUCHECK(c, cudaMallocHost(&c->h_status, cap * sizeof(int)));
+    CUCHECK(c, cudaMallocHost(&c->h_ids, cap * sizeof(int)));
+    CUCHECK(c, cudaMallocHost(&c->h_jit, cap * sizeof(double)));
+    c->h_cap = cap;
+    c->h_diag = nullptr;
+  }
+  if (c->h_diag) cudaFreeHost(c->h_diag);
+  CUCHECK(c, cudaMallocHost(&c->h_diag, cap * b.T * sizeof(double)));
+  c->bound = true;
+  return 0;
+}
+
+}  // extern "C"
+
+// Enqueue all phases for one chunk.  Phase events are recorded only when profiling is on.
+static void run_pipeline(b200gp_ctx* c, const Batch& b, int with_grad) {
+  cudaStream_t s = c->stream;
+  const bool prof = c->profiling;
+  cudaMemsetAsync(b.slot_status, 0, sizeof(int) * b.nslots, s);
+  if (prof) cudaEventRecord(c->ev[0], s);
+  launch_build_k(b, s);
+  if (prof) cudaEventRecord(c->ev[1], s);
+  for (int k = 0; k < b.T; k++) {
+    launch_potrf_diag(b, k, s);
+    if (k + 1 < b.T) {
+      launch_gemm(b, GM_TRSM, k, s);
+      launch_gemm(b, GM_SYRK, k, s);
+    }
+  }
+  if (prof) cudaEventRecord(c->ev[2], s);
+  for (int i = 1; i < b.T; i++) {
+    launch_gemm(b, GM_VACC, i, s);
+    launch_gemm(b, GM_VTRSM, i, s);
+  }
+  if (prof) cudaEventRecord(c->ev[3], s);
+  launch_solve(b, s);
+  if (prof) cudaEventRecord(c->ev[4], s);
+  if (with_grad) launch_gemm(b, GM_KINV, 0, s);
+  if (prof) cudaEventRecord(c->ev[5], s);
+  if (with_grad) launch_grad(b, s);
+  launch_finalize(b, with_grad, s);
+  if (prof) cudaEventRecord(c->ev[6], s);
+}
+
+static void collect_phase_ms(b200gp_ctx* c) {
+  if (!c->profiling) return;
+  cudaEventSynchronize(c->ev[6]);
+  for (int i = 0; i < 6; i++) cudaEventElapsedTime(&c->phase_ms[i], c->ev[i], c->ev[i + 1]);
+  c->n_phase = 6;
+}
+
+extern "C" {
+
+int b200gp_build_K(b200gp_ctx* c, const int32_t* prog, const int32_t* prog_off, const double* theta,
+                   const int32_t* theta_off, const int32_t* ids, int n, int add_diag, double* K_out) {
+  if (!c) return -1;
+  if (!c->bound) return fail(c, "b200gp_build_K: call b200gp_bind first");
+  if (!prog || !prog_off || !theta || !theta_off || !ids || !K_out) return fail(c, "b200gp_build_K: null pointer");
+  CUCHECK(c, cudaSetDevice(c->device));
+  const size_t n2 = (size_t)c->base.N * c->base.N;
+  for (int off = 0; off < n; off += c->slots) {
+    Batch b = c->base;
+    b.nslots = (n - off < c->slots) ? n - off : c->slots;
+    b.ids = ids + off;
+    b.prog = reinterpret_cast<const int4*>(prog); b.prog_off = prog_off; b.theta = theta; b.theta_off = theta_off;
+    b.quirks = c->quirks;
+    b.add_diag = add_diag;
+    launch_build_k(b, c->stream);
+    launch_export_sym(b, K_out + (size_t)off * n2, c->stream);
+  }
+  CUCHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int b200gp_lml_grad(b200gp_ctx* c, const int32_t* prog, const int32_t* prog_off, const double* theta,
+                    const int32_t* theta_off, const int32_t* ids, int n, int with_grad, double* lml, double* dlml,
+                    int32_t* status, int32_t* tries) {
+  if (!c) return -1;
+  if (!c->bound) return fail(c, "b200gp_lml_grad: call b200gp_bind first");
+  if (!prog || !prog_off || !theta || !theta_off || !ids || !lml || !status || (with_grad && !dlml))
+    return fail(c, "b200gp_lml_grad: null pointer");
+  CUCHECK(c, cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  for (int off = 0; off < n; off += c->slots) {
+    Batch b = c->base;
+    b.nslots = (n - off < c->slots) ? n - off : c->slots;
+    b.ids = ids + off;
+    b.prog = reinterpret_cast<const int4*>(prog); b.prog_off = prog_off; b.theta = theta; b.theta_off = theta_off;
+    b.lml = lml; b.dlml = dlml; b.status = status; b.tries = tries; b.try_no = 0;
+    b.jitter = nullptr;
+    b.quirks = c->quirks;
+    b.add_diag = 1;
+    run_pipeline(c, b, with_grad);
+    CUCHECK(c, cudaGetLastError());
+    CUCHECK(c, cudaMemcpyAsync(c->h_status, b.slot_status, sizeof(int) * b.nslots, cudaMemcpyDeviceToHost, s));
+    CUCHECK(c, cudaStreamSynchronize(s));
+    collect_phase_ms(c);
+    std::vector<int> failed;
+    for (int i = 0; i < b.nslots; i++)
+      if (c->h_status[i] != 0) failed.push_back(i);
+    if (failed.empty()) continue;
+
+    // GPy jitchol ladder (util/linalg.py): jitter = mean(diag(K_y)) * 1e-6 * 10^t, t = 0..4
+    CUCHECK(c, cudaMemcpyAsync(c->h_ids, b.ids, sizeof(int) * b.nslots, cudaMemcpyDeviceToHost, s));
+    CUCHECK(c, cudaMemcpyAsync(c->h_diag, b.diag_part, sizeof(double) * b.nslots * b.T, cudaMemcpyDeviceToHost, s));
+    CUCHECK(c, cudaStreamSynchronize(s));
+    std::vector<int> item(failed.size());
+    std::vector<double> dmean(failed.size());
+    for (size_t f = 0; f < failed.size(); f++) {
+      item[f] = c->h_ids[failed[f]];
+      double sum = 0.0;
+      for (int k = 0; k < b.T; k++) sum += c->h_diag[failed[f] * b.T + k];
+      dmean[f] = sum / b.N;
+    }
+    for (int t = 0; t < 5 && !item.empty(); t++) {
+      std::vector<int> it2;
+      std::vector<double> dm2;
+      int m = 0;
+      for (size_t f = 0; f < item.size(); f++) {
+        const double jit = dmean[f] * 1e-6 * std::pow(10.0, t);
+        if (!std::isfinite(jit)) continue;      // ladder stops for this item; status stays NOT_PD
+        c->h_ids[m] = item[f];
+        c->h_jit[m] = jit;
+        it2.push_back(item[f]);
+        dm2.push_back(dmean[f]);
+        m++;
+      }
+      if (m == 0) break;
+      CUCHECK(c, cudaMemcpyAsync(c->ws_ids, c->h_ids, sizeof(int) * m, cudaMemcpyHostToDevice, s));
+      CUCHECK(c, cudaMemcpyAsync(c->ws_jitter, c->h_jit, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+      Batch bf = b;
+      bf.nslots = m;
+      bf.ids = c->ws_ids;
+      bf.jitter = c->ws_jitter;
+      bf.try_no = t + 1;
+      run_pipeline(c, bf, with_grad);
+      CUCHECK(c, cudaGetLastError());
+      CUCHECK(c, cudaMemcpyAsync(c->h_status, bf.slot_status, sizeof(int) * m, cudaMemcpyDeviceToHost, s));
+      CUCHECK(c, cudaStreamSynchronize(s));
+      item.clear();
+      dmean.clear();
+      for (int i = 0; i < m; i++)
+        if (c->h_status[i] != 0) { item.push_back(it2[i]); dmean.push_back(dm2[i]); }
+    }
+  }
+  return 0;
+}
+
+size_t b200gp_potrf_work_bytes(int N) {
+  if (N <= 0 || N % NB != 0) return 0;
+  const size_t T = N / NB;
+  return T * NB * NB * sizeof(double) + T * sizeof(double) + 1024;
+}
+
+int b200gp_potrf(b200gp_ctx* c, double* dA, int N, void* work, double* logdet, int32_t* status) {
+  if (!c) return -1;
+  if (!dA || !work || !logdet || !status) return fail(c, "b200gp_potrf: null pointer");
+  if (N <= 0 || N % NB != 0) return fail(c, "b200gp_potrf: N must be a positive multiple of %d", NB);
+  CUCHECK(c, cudaSetDevice(c->device));
+  const int T = N / NB;
+  Carver cv(work);
+  Batch b{};
+  b.N = N; b.Np = N; b.T = T; b.D = 0; b.nslots = 1; b.mstride = (size_t)N * N;
+  b.M1 = dA; b.M2 = nullptr;
+  b.Dinv = cv.take<double>((size_t)T * NB * NB);
+  b.logdet_part = cv.take<double>(T);
+  b.slot_status = cv.take<int>(1);
+  cudaStream_t s = c->stream;
+  CUCHECK(c, cudaMemsetAsync(b.slot_status, 0, sizeof(int), s));
+  if (c->profiling) cudaEventRecord(c->ev[0], s);
+  for (int k = 0; k < T; k++) {
+    launch_potrf_diag(b, k, s);
+    if (k + 1 < T) {
+      launch_gemm(b, GM_TRSM, k, s);
+      launch_gemm(b, GM_SYRK, k, s);
+    }
+  }
+  if (c->profiling) cudaEventRecord(c->ev[1], s);
+  CUCHECK(c, cudaGetLastError());
+  std::vector<double> parts(T);
+  int st = 0;
+  CUCHECK(c, cudaMemcpyAsync(parts.data(), b.logdet_part, sizeof(double) * T, cudaMemcpyDeviceToHost, s));
+  CUCHECK(c, cudaMemcpyAsync(&st, b.slot_status, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUCHECK(c, cudaStreamSynchronize(s));
+  if (c->profiling) { cudaEventElapsedTime(&c->phase_ms[0], c->ev[0], c->ev[1]); c->n_phase = 1; }
+  double ld = 0.0;
+  if (st == 0) for (int k = 0; k < T; k++) ld += parts[k];
+  *logdet = st == 0 ? ld : NAN;
+  *status = st;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+// Blocked FP64 Cholesky, triangular inverse and K^-1 over batches of N x N matrices.
+//
+// Replaces LAPACK dpotrf / dtrtri / dpotri / dpotrs as GPy's `pdinv` + `dpotrs` call them inside
+// ExactGaussianInference.inference (reached from src/autoks/core/gp_model.py:64-65).
+//
+// Storage per slot: M1 (Np x Np row-major) holds K_y, then L in its lower tiles, finally K^-1 in its
+// lower tiles; M2 holds V = L^-T in its upper tiles; Dinv holds the T inverses of L's diagonal blocks.
+// Every blocked step is an "NT" tile GEMM (tile_gemm.cuh) or the in-register diagonal-block
+// factorisation (tile_potrf.cuh):
+//   right-looking Cholesky, step k:   POTRF(k);  L_ik = A_ik D_k^T (i>k);  A_ij -= L_ik L_jk^T (i>=j>k)
+//   V = L^-T, column i:               S_ji = sum_{k=j}^{i-1} V_jk L_ik^T;  V_ji = -S_ji D_i^T   (j<i), V_ii = D_i^T
+//   K^-1 (lower):                     (K^-1)_ij = sum_{k>=i} V_ik V_jk^T                            (i>=j)
+#include "kernels.cuh"
+#include "tile_gemm.cuh"
+#include "tile_potrf.cuh"
+
+namespace b200gp {
+
+// ------------------------------------------------------------------------------------------------
+// Diagonal block: L_kk = chol(A_kk), D_k = L_kk^-1, V_kk = D_k^T, logdet partial, PD status.
+// ------------------------------------------------------------------------------------------------
+constexpr int PD_LDL = NB + 1;
+constexpr int PD_SMEM_BYTES = NB * PD_LDL * 8 + (int)sizeof(TilePotrfSmem) + 64;
+
+__global__ void __launch_bounds__(TP_THREADS, 1) potrf_diag_kernel(Batch b, int k) {
+  const int slot = blockIdx.x;
+  if (b.slot_status[slot] != 0) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Lsm = reinterpret_cast<double*>(smem_raw);
+  TilePotrfSmem& S = *reinterpret_cast<TilePotrfSmem*>(smem_raw + NB * PD_LDL * 8);
+
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  double* A = b.M1 + slot * b.mstride + (size_t)(k * NB) * b.Np + k * NB;
+  double a[TP_R][TP_R];
+#pragma unroll
+  for (int p = 0; p < TP_R; p++)
+#pragma unroll
+    for (int q = 0; q < TP_R; q++) a[p][q] = A[(size_t)(ty + 16 * p) * b.Np + tx + 16 * q];
+
+  tile_potrf(a, S);
+  if (S.fail != 0) {   // uniform: S.fail was written before the last barrier inside tile_potrf
+    if (threadIdx.x == 0) b.slot_status[slot] = k * NB + S.fail;
+    return;
+  }
+  // log-determinant partial: sum_j log(pivot_j), reduced by warp 0 in a fixed order
+  if (threadIdx.x < 32) {
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < NB / 32; r++) s += log(S.piv[threadIdx.x + 32 * r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) b.logdet_part[slot * b.T + k] = s;
+  }
+  // L -> global (lower part of the tile; the strict upper part is zeroed) and -> shared for phase 2
+#pragma unroll
+  for (int p = 0; p < TP_R; p++)
+#pragma unroll
+    for (int q = 0; q < TP_R; q++) {
+      const int i = ty + 16 * p, c = tx + 16 * q;
+      const double v = (i >= c) ? a[p][q] : 0.0;
+      A[(size_t)i * b.Np + c] = v;
+      Lsm[i * PD_LDL + c] = v;
+    }
+  __syncthreads();
+  tile_trtri(a, Lsm, PD_LDL, S);
+  double* Dk = b.Dinv + ((size_t)slot * b.T + k) * (NB * NB);
+  __syncthreads();
+  // stage D in shared memory so the transposed copy (V_kk = D^T) is written coalesced as well
+#pragma unroll
+  for (int p = 0; p < TP_R; p++)
+#pragma unroll
+    for (int q = 0; q < TP_R; q++) {
+      const int i = ty + 16 * p, c = tx + 16 * q;
+      Dk[i * NB + c] = a[p][q];
+      Lsm[i * PD_LDL + c] = a[p][q];
+    }
+  if (b.M2 == nullptr) return;   // factor-only use (b200gp_potrf): no inverse wanted
+  double* V = b.M2 + slot * b.mstride + (size_t)(k * NB) * b.Np + k * NB;
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < TP_R; p++)
+#pragma unroll
+    for (int q = 0; q < TP_R; q++) {
+      const int i = ty + 16 * p, c = tx + 16 * q;
+      V[(size_t)i * b.Np + c] = Lsm[c * PD_LDL + i];
+    }
+}
+
+void launch_potrf_diag(const Batch& b, int k, cudaStream_t s) {
+  potrf_diag_kernel<<<b.nslots, TP_THREADS, PD_SMEM_BYTES, s>>>(b, k);
+  g_launch_count++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile GEMM phases
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TG_THREADS, 1) gemm_kernel(Batch b, int mode, int step) {
+  const int slot = blockIdx.y;
+  if (b.slot_status[slot] != 0) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* smem = reinterpret_cast<double*>(smem_raw);
+
+  double* M1 = b.M1 + slot * b.mstride;
+  double* M2 = b.M2 + slot * b.mstride;
+  const size_t ld = b.Np;
+  const double *A, *B;
+  double* C;
+  size_t ldb = ld;
+  int nchunks;
+  double alpha = 1.0, beta = 0.0;
+  const int bx = blockIdx.x;
+  switch (mode) {
+    case GM_TRSM: {        // L_ik = A_ik D_k^T
+      const int i = step + 1 + bx;
+      C = M1 + (size_t)(i * NB) * ld + step * NB;
+      A = C;
+      B = b.Dinv + ((size_t)slot * b.T + step) * (NB * NB);
+      ldb = NB;
+      nchunks = NB / TG_KC;
+      break;
+    }
+    case GM_SYRK: {        // A_ij -= L_ik L_jk^T
+      int r, c;
+      tri_decode(bx, r, c);
+      const int i = step + 1 + r, j = step + 1 + c;
+      C = M1 + (size_t)(i * NB) * ld + j * NB;
+      A = M1 + (size_t)(i * NB) * ld + step * NB;
+      B = M1 + (size_t)(j * NB) * ld + step * NB;
+      nchunks = NB / TG_KC;
+      alpha = -1.0; beta = -1.0;
+      break;
+    }
+    case GM_VACC: {        // S_ji = sum_{k=j}^{i-1} V_jk L_ik^T  (stored where V_ji will live)
+      const int i = step, j = bx;
+      C = M2 + (size_t)(j * NB) * ld + i * NB;
+      A = M2 + (size_t)(j * NB) * ld + j * NB;
+      B = M1 + (size_t)(i * NB) * ld + j * NB;
+      nchunks = (i - j) * (NB / TG_KC);
+      break;
+    }
+    case GM_VTRSM: {       // V_ji = -S_ji D_i^T
+      const int i = step, j = bx;
+      C = M2 + (size_t)(j * NB) * ld + i * NB;
+      A = C;
+      B = b.Dinv + ((size_t)slot * b.T + i) * (NB * NB);
+      ldb = NB;
+      nchunks = NB / TG_KC;
+      alpha = -1.0;
+      break;
+    }
+    default: {             // GM_KINV: (K^-1)_ij = sum_{k>=i} V_ik V_jk^T
+      int i, j;
+      tri_decode(bx, i, j);
+      C = M1 + (size_t)(i * NB) * ld + j * NB;
+      A = M2 + (size_t)(i * NB) * ld + i * NB;
+      B = M2 + (size_t)(j * NB) * ld + i * NB;
+      nchunks = (b.T - i) * (NB / TG_KC);
+      break;
+    }
+  }
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, tg = lane & 3;
+  double* Cw = C + (size_t)(wm * 64 + g) * ld + wn * 32 + tg * 2;
+
+  double acc[8][4][2];
+  if (beta != 0.0) {       // accumulators start at beta*C so the C read overlaps the pipeline fill
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        const double2 v = *reinterpret_cast<const double2*>(Cw + (size_t)(mt * 8) * ld + nt * 8);
+        acc[mt][nt][0] = beta * v.x;
+        acc[mt][nt][1] = beta * v.y;
+      }
+  } else {
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+  }
+
+  tile_gemm_nt(acc, A, ld, B, ldb, nchunks, smem);
+
+#pragma unroll
+  for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+      double2 v;
+      v.x = alpha * acc[mt][nt][0];
+      v.y = alpha * acc[mt][nt][1];
+      *reinterpret_cast<double2*>(Cw + (size_t)(mt * 8) * ld + nt * 8) = v;
+    }
+}
+
+void launch_gemm(const Batch& b, int mode, int step, cudaStream_t s) {
+  int ntiles = 0;
+  switch (mode) {
+    case GM_TRSM: ntiles = b.T - step - 1; break;
+    case GM_SYRK: ntiles = tri_count(b.T - step - 1); break;
+    case GM_VACC: ntiles = step; break;
+    case GM_VTRSM: ntiles = step; break;
+    default: ntiles = tri_count(b.T); break;
+  }
+  if (ntiles <= 0) return;
+  dim3 grid(ntiles, b.nslots);
+  gemm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, mode, step);
+  g_launch_count++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// z = V^T y (= L^-1 y),  alpha = V z (= L^-T z)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) zsolve_kernel(Batch b) {
+  const int slot = blockIdx.y, i = blockIdx.x;
+  if (b.slot_status[slot] != 0) return;
+  __shared__ double red[256];
+  const int c = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const double* V = b.M2 + slot * b.mstride + i * NB + c;
+  const int rows = (i + 1) * NB;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  int r = half;
+  for (; r + 6 < rows; r += 8) {
+    s0 = fma(V[(size_t)r * b.Np], b.y[r], s0);
+    s1 = fma(V[(size_t)(r + 2) * b.Np], b.y[r + 2], s1);
+    s2 = fma(V[(size_t)(r + 4) * b.Np], b.y[r + 4], s2);
+    s3 = fma(V[(size_t)(r + 6) * b.Np], b.y[r + 6], s3);
+  }
+  for (; r < rows; r += 2) s0 = fma(V[(size_t)r * b.Np], b.y[r], s0);
+  red[threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (half == 0) b.z[(size_t)slot * b.Np + i * NB + c] = red[c] + red[c + 128];
+}
+
+__global__ void __launch_bounds__(256) alpha_kernel(Batch b) {
+  const int slot = blockIdx.y, j = blockIdx.x;
+  if (b.slot_status[slot] != 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double* z = b.z + (size_t)slot * b.Np;
+  for (int rr = warp; rr < NB; rr += 8) {
+    const int r = j * NB + rr;
+    const double* Vr = b.M2 + slot * b.mstride + (size_t)r * b.Np;
+    double s = 0.0;
+    for (int c = j * NB + lane * 2; c < b.Np; c += 64) {
+      const double2 v = *reinterpret_cast<const double2*>(Vr + c);
+      const double2 zz = *reinterpret_cast<const double2*>(z + c);
+      s = fma(v.x, zz.x, s);
+      s = fma(v.y, zz.y, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) b.alpha[(size_t)slot * b.Np + r] = s;
+  }
+}
+
+void launch_solve(const Batch& b, cudaStream_t s) {
+  dim3 grid(b.T, b.nslots);
+  zsolve_kernel<<<grid, 256, 0, s>>>(b);
+  alpha_kernel<<<grid, 256, 0, s>>>(b);
+  g_launch_count += 2;
+}
+
+int configure_chol_kernels() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  return 0;
+}
+
+}  // namespace b200gp

@@ -1,0 +1,55 @@
+// Internal launch interface between the C-ABI layer (api.cu) and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace b200gp {
+
+// Device-side view of one batch of `nslots` matrices being scored together.
+struct Batch {
+  // geometry
+  int N, Np, T, D;
+  int nslots;
+  size_t mstride;            // Np * Np
+  // per-slot scratch (slot-major)
+  double* M1;                // K -> L (lower) -> K^-1 (lower)
+  double* M2;                // V = L^-T (upper)
+  double* Dinv;              // [slot][T][NB*NB] inverses of the diagonal blocks of L
+  double* z;                 // [slot][Np]  L^-1 y
+  double* alpha;             // [slot][Np]  K^-1 y
+  double* logdet_part;       // [slot][T]
+  double* diag_part;         // [slot][T]   partial sums of diag(K_y) (jitter ladder)
+  double* grad_part;         // [slot][ntiles][pstride]
+  int pstride;
+  int* slot_status;          // [slot] 0 ok, >0 = 1-based index of first bad pivot
+  // shared data
+  const double* Xt;          // [D][Np] dimension-major, zero padded
+  const double* y;           // [Np] zero padded
+  // per-item inputs / outputs (indexed through ids[slot])
+  const int* ids;
+  const int4* prog;
+  const int* prog_off;
+  const double* theta;
+  const int* theta_off;
+  const double* jitter;      // [slot] extra diagonal jitter (jitchol ladder), may be null
+  double* lml;               // [item]
+  double* dlml;              // [theta layout]
+  int* status;               // [item]
+  int* tries;                // [item] jitter-ladder tries used (may be null)
+  int try_no;                // ladder step of this pipeline run (0 = plain)
+  int quirks;
+  int add_diag;              // 1: add noise + 1e-8 + jitter to the diagonal (K_y); 0: bare kern.K
+};
+
+enum GemmMode : int { GM_TRSM = 0, GM_SYRK = 1, GM_VACC = 2, GM_VTRSM = 3, GM_KINV = 4 };
+
+void launch_build_k(const Batch& b, cudaStream_t s);
+void launch_export_sym(const Batch& b, double* out, cudaStream_t s);       // out[slot][N][N] symmetric copy of M1
+void launch_potrf_diag(const Batch& b, int k, cudaStream_t s);
+void launch_gemm(const Batch& b, int mode, int step, cudaStream_t s);
+void launch_solve(const Batch& b, cudaStream_t s);                          // z = L^-1 y, alpha = L^-T z
+void launch_grad(const Batch& b, cudaStream_t s);
+void launch_finalize(const Batch& b, int with_grad, cudaStream_t s);
+int configure_kernels();
+extern long long g_launch_count;                                            // kernels launched (host-side counter)                                                    // opt-in shared memory sizes
+
+}  // namespace b200gp

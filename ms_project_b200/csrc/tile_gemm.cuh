@@ -1,0 +1,91 @@
+// 128x128 FP64 tile GEMM on the DMMA tensor pipe:  acc(128x128) += A(128 x K) * B(128 x K)^T
+//
+// Both operands are row-major with K contiguous ("NT"), which is how every blocked phase of the
+// Cholesky / inverse is arranged (see chol_kernels.cu).  Blackwell's tcgen05/UMMA has no FP64 kind;
+// the FP64 tensor path on sm_100a is `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4, measured 36.9 TFLOP/s
+// register-resident, profiles/fp64_peaks_r01.json), so this is a warp-level MMA kernel:
+//   * 256 threads = 8 warps in a 2 (M) x 4 (N) grid, warp tile 64 x 32 = 8 x 4 DMMA tiles
+//   * operands stream global -> shared through a 4-stage cp.async (LDGSTS) ring, 16 doubles of K
+//     per stage, rows padded to 20 doubles so the 64-bit fragment loads are bank-conflict free
+//   * one __syncthreads per stage
+#pragma once
+#include "common.cuh"
+
+namespace b200gp {
+
+constexpr int TG_THREADS = 256;
+constexpr int TG_KC = 16;                 // K elements per pipeline stage
+constexpr int TG_LDK = TG_KC + 4;         // padded row length in shared memory (doubles)
+constexpr int TG_STAGES = 4;
+constexpr int TG_STAGE_DOUBLES = 2 * NB * TG_LDK;                       // A + B per stage
+constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_DOUBLES * 8;         // 163,840 B
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Issue the cp.async copies of one K-chunk (A rows and B rows, 128 x 16 doubles each).
+__device__ __forceinline__ void tg_load_stage(double* stage, const double* __restrict__ A, size_t lda,
+                                              const double* __restrict__ B, size_t ldb, int koff) {
+  double* As = stage;
+  double* Bs = stage + NB * TG_LDK;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int seg = threadIdx.x + TG_THREADS * r;   // 1024 16-byte segments per operand
+    const int row = seg >> 3, part = (seg & 7) * 2;
+    cp_async16(As + row * TG_LDK + part, A + (size_t)row * lda + koff + part);
+    cp_async16(Bs + row * TG_LDK + part, B + (size_t)row * ldb + koff + part);
+  }
+}
+
+// acc[mt][nt][2]: C fragment of DMMA tile (mt, nt) of this warp's 64x32 sub-tile.
+// Element (row, col) of the CTA tile held in acc[mt][nt][e]:
+//   row = wm*64 + mt*8 + (lane>>2),  col = wn*32 + nt*8 + (lane&3)*2 + e
+__device__ __forceinline__ void tile_gemm_nt(double (&acc)[8][4][2], const double* __restrict__ A, size_t lda,
+                                             const double* __restrict__ B, size_t ldb, int nchunks, double* smem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int g = lane >> 2, tg = lane & 3;
+
+#pragma unroll
+  for (int s = 0; s < TG_STAGES - 1; s++) {
+    if (s < nchunks) tg_load_stage(smem + s * TG_STAGE_DOUBLES, A, lda, B, ldb, s * TG_KC);
+    cp_async_commit();
+  }
+  for (int kc = 0; kc < nchunks; kc++) {
+    cp_async_wait<TG_STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kc + TG_STAGES - 1;
+      if (nk < nchunks) tg_load_stage(smem + (nk % TG_STAGES) * TG_STAGE_DOUBLES, A, lda, B, ldb, nk * TG_KC);
+      cp_async_commit();
+    }
+    const double* As = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + (wm * 64 + g) * TG_LDK + tg;
+    const double* Bs = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + NB * TG_LDK + (wn * 32 + g) * TG_LDK + tg;
+#pragma unroll
+    for (int kk = 0; kk < TG_KC; kk += 4) {
+      double a[8], b[4];
+#pragma unroll
+      for (int mt = 0; mt < 8; mt++) a[mt] = As[mt * 8 * TG_LDK + kk];
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) b[nt] = Bs[nt * 8 * TG_LDK + kk];
+#pragma unroll
+      for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+}  // namespace b200gp

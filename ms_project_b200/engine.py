@@ -1,0 +1,220 @@
+"""Device engine: owns one libb200gp context per GPU, the torch-allocated workspace and the staging of
+programs / hyperparameters.  PyTorch is used for device memory, streams and copies only."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .program import ProgramBatch
+
+_ENGINES = {}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.B200GPError('no CUDA device: ms_project_b200 has no CPU fallback')
+    return torch
+
+
+class Engine(object):
+    """One per GPU.  `bind` the (standardised) training data once per search, then score batches."""
+
+    def __init__(self, device=0):
+        torch = _torch()
+        self.torch = torch
+        self.device = torch.device('cuda', device)
+        self.lib = _lib.lib()
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.current_stream(self.device)
+        ctx = ctypes.c_void_p()
+        rc = self.lib.b200gp_create(device, ctypes.c_void_p(self.stream.cuda_stream), ctypes.byref(ctx))
+        if rc != 0:
+            raise _lib.B200GPError('b200gp_create failed (rc=%d): needs an sm_100 GPU' % rc)
+        self.ctx = ctx
+        self.N = self.D = 0
+        self.slots = 0
+        self.max_params = 0
+        self._ws = None
+        self._X = self._y = None
+        self._X_host = None
+
+    def close(self):
+        if getattr(self, 'ctx', None):
+            self.lib.b200gp_destroy(self.ctx)
+            self.ctx = None
+
+    # ------------------------------------------------------------------ configuration
+    def set_quirks(self, mask):
+        _lib.check(self.ctx, self.lib.b200gp_set_quirks(self.ctx, int(mask)), 'b200gp_set_quirks')
+
+    def set_profiling(self, on):
+        _lib.check(self.ctx, self.lib.b200gp_set_profiling(self.ctx, int(bool(on))), 'b200gp_set_profiling')
+
+    def launch_count(self):
+        return int(self.lib.b200gp_launch_count(self.ctx))
+
+    def last_phase_ms(self):
+        buf = (ctypes.c_float * 8)()
+        n = self.lib.b200gp_last_phase_ms(self.ctx, buf, 8)
+        return [float(buf[i]) for i in range(max(n, 0))]
+
+    def slots_for(self, N, D, n_items, max_params, mem_fraction=0.8):
+        """Largest batch the free HBM holds (180 GB / GPU on B200), capped at the number of items."""
+        free, _total = self.torch.cuda.mem_get_info(self.device)
+        per_slot = self.lib.b200gp_workspace_bytes(N, D, 2, max_params) - self.lib.b200gp_workspace_bytes(N, D, 1, max_params)
+        fixed = self.lib.b200gp_workspace_bytes(N, D, 1, max_params) - per_slot
+        budget = int(free * mem_fraction) - fixed
+        return int(max(1, min(n_items, budget // max(per_slot, 1))))
+
+    def bind(self, X, y, slots, max_params=32):
+        """X: N x D, y: N or N x 1 (host numpy, already standardised by the caller)."""
+        torch = self.torch
+        X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64)).reshape(-1)
+        if X.ndim != 2 or X.shape[0] != y.shape[0]:
+            raise ValueError('X must be N x D and y must have N entries')
+        N, D = X.shape
+        nbytes = self.lib.b200gp_workspace_bytes(N, D, int(slots), int(max_params))
+        if nbytes == 0:
+            raise ValueError('invalid workspace geometry')
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._X = torch.from_numpy(X).to(self.device)
+        self._y = torch.from_numpy(y).to(self.device)
+        self._X_host = X
+        rc = self.lib.b200gp_bind(self.ctx, self._ws.data_ptr(), self._ws.numel(), int(slots), int(max_params),
+                                  self._X.data_ptr(), N, D, self._y.data_ptr())
+        _lib.check(self.ctx, rc, 'b200gp_bind')
+        self.N, self.D, self.slots, self.max_params = N, D, int(slots), int(max_params)
+
+    # ------------------------------------------------------------------ program staging
+    def upload_programs(self, batch):
+        """ProgramBatch -> device tensors (kept on the batch object)."""
+        torch = self.torch
+        if batch.max_params > self.max_params:
+            raise ValueError('batch has kernels with %d parameters; engine bound for %d' % (batch.max_params, self.max_params))
+        if batch.max_dim >= self.D:
+            raise ValueError('a kernel uses input dimension %d but X has %d columns' % (batch.max_dim, self.D))
+        batch.d_tokens = torch.from_numpy(batch.tokens.reshape(-1)).to(self.device)
+        batch.d_prog_off = torch.from_numpy(batch.prog_off).to(self.device)
+        batch.d_theta_off = torch.from_numpy(batch.theta_off).to(self.device)
+        n, nt = batch.n_items, int(batch.theta_off[-1])
+        batch.d_theta = torch.empty(nt, dtype=torch.float64, device=self.device)
+        batch.d_lml = torch.empty(n, dtype=torch.float64, device=self.device)
+        batch.d_dlml = torch.empty(nt, dtype=torch.float64, device=self.device)
+        batch.d_status = torch.empty(n, dtype=torch.int32, device=self.device)
+        batch.d_tries = torch.empty(n, dtype=torch.int32, device=self.device)
+        batch.h_theta = torch.empty(nt, dtype=torch.float64).pin_memory()
+        batch.h_out = torch.empty(n + nt, dtype=torch.float64).pin_memory()
+        batch.h_int = torch.empty(2 * n, dtype=torch.int32).pin_memory()
+        batch.d_out = torch.empty(n + nt, dtype=torch.float64, device=self.device)
+        batch.d_int = torch.empty(2 * n, dtype=torch.int32, device=self.device)
+        batch.d_all_ids = torch.arange(n, dtype=torch.int32, device=self.device)
+        batch.engine = self
+        return batch
+
+    # ------------------------------------------------------------------ scoring
+    def lml_grad(self, batch, theta, ids=None, with_grad=True):
+        """Evaluate items `ids` (default: all) of an uploaded batch at the flat host `theta`
+        (device layout, see ProgramBatch.pack_theta).  Host buffers in, host results out:
+        returns (lml[n_items], dlml[theta layout], status[n_items], tries[n_items]); entries of items not
+        in `ids` are left untouched from the previous call."""
+        torch = self.torch
+        n = batch.n_items
+        batch.h_theta.numpy()[:] = theta
+        batch.d_theta.copy_(batch.h_theta, non_blocking=True)
+        if ids is None:
+            d_ids, n_act = batch.d_all_ids, n
+        else:
+            ids = np.ascontiguousarray(np.asarray(ids, dtype=np.int32))
+            n_act = int(ids.size)
+            d_ids = torch.from_numpy(ids).to(self.device, non_blocking=True)
+        if n_act == 0:
+            return (batch.h_out.numpy()[:n], batch.h_out.numpy()[n:], batch.h_int.numpy()[:n], batch.h_int.numpy()[n:])
+        d_lml, d_dlml = batch.d_out[:n], batch.d_out[n:]
+        d_status, d_tries = batch.d_int[:n], batch.d_int[n:]
+        rc = self.lib.b200gp_lml_grad(self.ctx, batch.d_tokens.data_ptr(), batch.d_prog_off.data_ptr(),
+                                      batch.d_theta.data_ptr(), batch.d_theta_off.data_ptr(), d_ids.data_ptr(), n_act,
+                                      int(bool(with_grad)), d_lml.data_ptr(), d_dlml.data_ptr(), d_status.data_ptr(),
+                                      d_tries.data_ptr())
+        _lib.check(self.ctx, rc, 'b200gp_lml_grad')
+        batch.h_out.copy_(batch.d_out, non_blocking=True)
+        batch.h_int.copy_(batch.d_int, non_blocking=True)
+        self.stream.synchronize()
+        out = batch.h_out.numpy()
+        ints = batch.h_int.numpy()
+        return out[:n], out[n:], ints[:n], ints[n:]
+
+    def lml_grad_device(self, batch, ids=None, with_grad=True):
+        """Same evaluation with theta already in `batch.d_theta`; results stay on the device
+        (batch.d_out / batch.d_int).  Used by bench.py for the HBM-resident timing."""
+        n = batch.n_items
+        if ids is None:
+            d_ids, n_act = batch.d_all_ids, n
+        else:
+            d_ids, n_act = ids, int(ids.numel())
+        rc = self.lib.b200gp_lml_grad(self.ctx, batch.d_tokens.data_ptr(), batch.d_prog_off.data_ptr(),
+                                      batch.d_theta.data_ptr(), batch.d_theta_off.data_ptr(), d_ids.data_ptr(), n_act,
+                                      int(bool(with_grad)), batch.d_out[:n].data_ptr(), batch.d_out[n:].data_ptr(),
+                                      batch.d_int[:n].data_ptr(), batch.d_int[n:].data_ptr())
+        _lib.check(self.ctx, rc, 'b200gp_lml_grad')
+
+    def build_K(self, batch, theta, ids=None, add_diag=False):
+        """Dense kernel matrices (n x N x N, host numpy) of the selected items over the bound X."""
+        torch = self.torch
+        batch.h_theta.numpy()[:] = theta
+        batch.d_theta.copy_(batch.h_theta, non_blocking=True)
+        if ids is None:
+            d_ids, n_act = batch.d_all_ids, batch.n_items
+        else:
+            ids = np.ascontiguousarray(np.asarray(ids, dtype=np.int32))
+            n_act = int(ids.size)
+            d_ids = torch.from_numpy(ids).to(self.device)
+        out = torch.empty((n_act, self.N, self.N), dtype=torch.float64, device=self.device)
+        rc = self.lib.b200gp_build_K(self.ctx, batch.d_tokens.data_ptr(), batch.d_prog_off.data_ptr(),
+                                     batch.d_theta.data_ptr(), batch.d_theta_off.data_ptr(), d_ids.data_ptr(), n_act,
+                                     int(bool(add_diag)), out.data_ptr())
+        _lib.check(self.ctx, rc, 'b200gp_build_K')
+        return out.cpu().numpy()
+
+    def potrf(self, A):
+        """In-place blocked Cholesky of a device tensor A (N x N float64, N % 128 == 0).
+        Returns (logdet, status)."""
+        torch = self.torch
+        N = A.shape[0]
+        wb = self.lib.b200gp_potrf_work_bytes(N)
+        if wb == 0:
+            raise ValueError('N must be a positive multiple of 128')
+        work = torch.empty(wb, dtype=torch.uint8, device=self.device)
+        ld = ctypes.c_double()
+        st = ctypes.c_int32()
+        rc = self.lib.b200gp_potrf(self.ctx, A.data_ptr(), N, work.data_ptr(), ctypes.byref(ld), ctypes.byref(st))
+        _lib.check(self.ctx, rc, 'b200gp_potrf')
+        return ld.value, st.value
+
+
+def get_engine(device=0, role='search'):
+    """Engines are cached per (device, role); 'adhoc' serves one-off kern.K calls so that a search's
+    bound data is never disturbed."""
+    key = (device, role)
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine(device)
+    return _ENGINES[key]
+
+
+def kernel_matrix(kernel, X, X2=None):
+    """kern.K(X, X2) on the device (compute_kernel, src/autoks/backend/kernel.py:317-322)."""
+    X = np.asarray(X, dtype=np.float64)
+    if X2 is not None and (X2 is not X) and not (X2.shape == X.shape and np.array_equal(X2, X)):
+        raise NotImplementedError('cross-covariances K(X, X2 != X) go through the posterior path (SURVEY.md 8f, f4)')
+    eng = get_engine(0, 'adhoc')
+    batch = ProgramBatch([kernel])
+    eng.bind(X, np.zeros(X.shape[0]), slots=1, max_params=max(batch.max_params, 1))
+    eng.upload_programs(batch)
+    return eng.build_K(batch, batch.initial_theta(), add_diag=False)[0]
+
+
+def kernel_diag(kernel, X):
+    return np.diag(kernel_matrix(kernel, X)).copy()

@@ -1,0 +1,106 @@
+"""GPU parity: LML / gradients / kernel matrices of the CUDA path against the NumPy oracle.
+Tolerances are the north star's: NLML rel <= 1e-8, gradients rel <= 1e-6."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import to_oracle_expr, from_string, make_data
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ['SE_1', 'RQ_1', 'PER_1', 'LIN_1', 'SE_1 + RQ_2', 'SE_1 * PER_1 + RQ_2', '(SE_1 + RQ_2) * LIN_2',
+           'SE_1 * SE_2 * RQ_1 + PER_2 * LIN_1 + CONST_1', 'LIN_1 * LIN_1 * PER_1', '(SE_1 + PER_2) * (RQ_1 + LIN_2)']
+
+
+def random_theta(batch, rng, lo=-0.7, hi=0.7):
+    ks = [np.exp(rng.uniform(lo, hi, size=int(p))) for p in batch.n_params]
+    nz = np.exp(rng.uniform(-3, -0.5, size=batch.n_items))
+    return batch.pack_theta(ks, nz), ks, nz
+
+
+@pytest.mark.parametrize('n,d', [(5, 2), (100, 2), (128, 2), (300, 3), (513, 2)])
+def test_lml_grad_matches_oracle(engine, n, d):
+    from ms_project_b200.program import ProgramBatch
+    from oracle import gp
+    X, y = make_data(n, d, seed=n)
+    kernels = [from_string(s) for s in KERNELS]
+    batch = ProgramBatch(kernels)
+    engine.bind(X, y, slots=4, max_params=batch.max_params)     # 4 slots < 10 items: exercises chunking
+    engine.upload_programs(batch)
+    theta, ks, nz = random_theta(batch, np.random.RandomState(1))
+    lml, dlml, status, tries = engine.lml_grad(batch, theta)
+    for i, k in enumerate(kernels):
+        ref_lml, ref_g, _ = gp.lml_and_grad(to_oracle_expr(k), ks[i], nz[i], X, y)
+        a, b = batch.theta_off[i], batch.theta_off[i + 1]
+        assert status[i] == 0 and tries[i] == 0
+        assert abs(lml[i] - ref_lml) <= 1e-8 * max(1.0, abs(ref_lml)), (KERNELS[i], lml[i], ref_lml)
+        scale = max(1.0, np.max(np.abs(ref_g)))
+        assert np.max(np.abs(dlml[a:b] - ref_g)) <= 1e-6 * scale, (KERNELS[i], dlml[a:b], ref_g)
+
+
+def test_kernel_matrix_matches_oracle_and_gpml(engine):
+    from ms_project_b200.program import ProgramBatch
+    from oracle import kernels as ok
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'gpml_kernels.json')))
+    X = np.array(gold['X'], dtype=np.float64).reshape(-1, 1)
+    for case in gold['cases']:
+        k = from_string(case['kernel'])
+        batch = ProgramBatch([k])
+        engine.bind(X, np.zeros(5), slots=1, max_params=batch.max_params)
+        engine.upload_programs(batch)
+        theta = batch.pack_theta([np.array(case['theta'])], [0.0])
+        K = engine.build_K(batch, theta)[0]
+        assert np.allclose(K, np.array(case['K']), rtol=1e-8, atol=1e-8), case['kernel']
+        assert np.allclose(K, ok.K(ok.parse(case['kernel']), case['theta'], X), rtol=1e-13, atol=1e-13)
+
+
+def test_subset_ids_and_quirks(engine):
+    from ms_project_b200.program import ProgramBatch
+    from oracle import gp
+    X, y = make_data(200, 2, seed=3)
+    kernels = [from_string(s) for s in ['PER_1', 'LIN_2 + SE_1', 'RQ_2']]
+    batch = ProgramBatch(kernels)
+    engine.bind(X, y, slots=8, max_params=batch.max_params)
+    engine.upload_programs(batch)
+    theta, ks, nz = random_theta(batch, np.random.RandomState(2))
+    engine.set_quirks(3)
+    try:
+        lml, dlml, status, _ = engine.lml_grad(batch, theta, ids=[1, 0])
+        for i in (0, 1):
+            ref_lml, ref_g, _ = gp.lml_and_grad(to_oracle_expr(kernels[i]), ks[i], nz[i], X, y, quirks=True)
+            a, b = batch.theta_off[i], batch.theta_off[i + 1]
+            assert abs(lml[i] - ref_lml) <= 1e-8 * max(1.0, abs(ref_lml))
+            assert np.max(np.abs(dlml[a:b] - ref_g)) <= 1e-6 * max(1.0, np.max(np.abs(ref_g)))
+    finally:
+        engine.set_quirks(0)
+
+
+def test_jitter_ladder_and_not_pd(engine):
+    """GPy's jitchol ladder.  Item 0: K_y = v 11^T exactly (SE with an enormous lengthscale; v = 1e12 swallows the
+    noise), so the second pivot is exactly 0 on any IEEE implementation and the first rung (mean(diag) * 1e-6)
+    repairs it.  Item 1 is healthy.  Item 2 has a NaN hyperparameter: every rung fails -> NOT_PD / NaN."""
+    from ms_project_b200.program import ProgramBatch
+    from oracle import gp
+    rng = np.random.RandomState(0)
+    X = rng.randn(160, 1)
+    y = rng.randn(160, 1)
+    kernels = [from_string('SE_1'), from_string('SE_1 + RQ_1'), from_string('RQ_1')]
+    batch = ProgramBatch(kernels)
+    engine.bind(X, y, slots=3, max_params=batch.max_params)
+    engine.upload_programs(batch)
+    ks = [np.array([1e12, 1e9]), np.array([1.0, 1.0, 1.0, 1.0, 2.0]), np.array([1.0, np.nan, 2.0])]
+    nz = [1e-12, 0.1, 0.1]
+    theta = batch.pack_theta(ks, nz)
+    lml, dlml, status, tries = engine.lml_grad(batch, theta)
+    ref_lml, ref_g, inf = gp.lml_and_grad(to_oracle_expr(kernels[0]), ks[0], nz[0], X, y)
+    assert inf['tries'] == 1
+    assert status[0] == 1 and tries[0] == 1
+    assert abs(lml[0] - ref_lml) <= 1e-8 * abs(ref_lml)
+    a, b = batch.theta_off[0], batch.theta_off[1]
+    assert np.max(np.abs(dlml[a:b] - ref_g)) <= 1e-6 * max(1.0, np.max(np.abs(ref_g)))
+    assert status[1] == 0 and tries[1] == 0
+    assert status[2] == 2 and np.isnan(lml[2])
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.lml_and_grad(to_oracle_expr(kernels[2]), ks[2], nz[2], X, y)
