@@ -19,4 +19,4 @@ paramz.  Neither is vendored in /root/reference nor installable here, so:
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs
 may import this package.  The product (`ms_project_b200`) never does.
 """
-from . import kernels, gp, model, hellinger, scoring  # noqa: F401
+from . import kernels, gp, model, hellinger, scoring, adapter  # noqa: F401

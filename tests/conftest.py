@@ -13,14 +13,7 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
-def to_oracle_expr(kernel):
-    """Product kernel object -> oracle expression tree (tests only: the two sides share no code)."""
-    from ms_project_b200.gpy_compat.kern import Add, Prod
-    if isinstance(kernel, Add):
-        return ('+', [to_oracle_expr(p) for p in kernel.parts])
-    if isinstance(kernel, Prod):
-        return ('*', [to_oracle_expr(p) for p in kernel.parts])
-    return (kernel.op_name, int(kernel.active_dims[0]))
+from oracle.adapter import to_oracle_expr  # noqa: E402,F401
 
 
 def from_string(s):
