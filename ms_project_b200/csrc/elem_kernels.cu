@@ -45,24 +45,20 @@ __global__ void __launch_bounds__(256) build_k_kernel(Batch b) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* out = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB;
   double dsum = 0.0;
-  for (int r = warp; r < NB; r += 8) {
-    const int gi = ti * NB + r;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int c = h * 64 + lane * 2;
-      double v[2];
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int gj = tj * NB + c + e;
-        if (gi >= b.N || gj >= b.N) {
-          v[e] = (gi == gj) ? 1.0 : 0.0;
-        } else {
-          v[e] = eval_K(S.P, S.xi + r, S.xj + c + e, NB);
-          if (gi == gj) { v[e] += diag_add; dsum += v[e]; }
-        }
-      }
-      *reinterpret_cast<double2*>(out + (size_t)r * b.Np + c) = make_double2(v[0], v[1]);
+  // thread -> 64 elements: rows warp + 8k (k < 16), columns lane + 32m (m < 4): every warp store is one
+  // 256-byte row segment.  One copy of the interpreter in the instruction stream (no unrolling).
+#pragma unroll 1
+  for (int it = 0; it < 64; it++) {
+    const int r = warp + 8 * (it >> 2), c = lane + 32 * (it & 3);
+    const int gi = ti * NB + r, gj = tj * NB + c;
+    double v;
+    if (gi >= b.N || gj >= b.N) {
+      v = (gi == gj) ? 1.0 : 0.0;
+    } else {
+      v = eval_K(S.P, S.xi + r, S.xj + c, NB);
+      if (gi == gj) { v += diag_add; dsum += v; }
     }
+    out[(size_t)r * b.Np + c] = v;
   }
   if (ti == tj) {   // deterministic partial of trace(K_y) for the jitter ladder
     S.red[threadIdx.x] = dsum;
@@ -122,23 +118,18 @@ __global__ void __launch_bounds__(256) grad_kernel(Batch b) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double* Kinv = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB;
-  for (int r = warp; r < NB; r += 8) {
-    const int gi = ti * NB + r;
-    if (gi >= b.N) break;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int c = h * 64 + lane * 2;
-      const double2 kv = *reinterpret_cast<const double2*>(Kinv + (size_t)r * b.Np + c);
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int gj = tj * NB + c + e;
-        if (gj >= b.N || gj > gi) continue;
-        double w = 0.5 * (S.ai[r] * S.aj[c + e] - (e == 0 ? kv.x : kv.y));
-        if (gi == gj) acc[np] += w;     // dL/d(noise) = trace(dL/dK)
-        else w *= 2.0;                  // symmetric pair (i, j) and (j, i)
-        eval_grad(S.P, S.xi + r, S.xj + c + e, NB, w, acc, b.quirks);
-      }
-    }
+  double kv_next = Kinv[(size_t)warp * b.Np + lane];
+#pragma unroll 1
+  for (int it = 0; it < 64; it++) {
+    const int r = warp + 8 * (it >> 2), c = lane + 32 * (it & 3);
+    const double kv = kv_next;
+    if (it + 1 < 64) kv_next = Kinv[(size_t)(warp + 8 * ((it + 1) >> 2)) * b.Np + lane + 32 * ((it + 1) & 3)];
+    const int gi = ti * NB + r, gj = tj * NB + c;
+    if (gi >= b.N || gj >= b.N || gj > gi) continue;
+    double w = 0.5 * (S.ai[r] * S.aj[c] - kv);
+    if (gi == gj) acc[np] += w;     // dL/d(noise) = trace(dL/dK)
+    else w *= 2.0;                  // symmetric pair (i, j) and (j, i)
+    eval_grad(S.P, S.xi + r, S.xj + c, NB, w, acc, b.quirks);
   }
   for (int p = 0; p <= np; p++) {
     double v = acc[p];

@@ -13,6 +13,7 @@ namespace b200gp {
 struct ProgSmem {
   int4 tok[MAX_TOKENS];
   double cst[MAX_TOKENS][4];   // per-leaf derived constants (reciprocals hoisted out of the N^2 loop)
+  double ivar[MAX_TOKENS];     // 1 / variance of each leaf (dK/dvariance = K / variance)
   int ntok;
   int nparam;                  // kernel parameters (noise excluded)
   double noise;                // Gaussian_noise.variance
@@ -39,6 +40,7 @@ __device__ inline void load_program(ProgSmem& P, const int4* __restrict__ prog, 
       }
     }
     P.cst[t][0] = c0; P.cst[t][1] = c1; P.cst[t][2] = c2; P.cst[t][3] = c3;
+    P.ivar[t] = (k.x <= OP_CONST) ? 1.0 / c0 : 0.0;
   }
   if (threadIdx.x == 0) {
     P.ntok = nt;
@@ -49,7 +51,7 @@ __device__ inline void load_program(ProgSmem& P, const int4* __restrict__ prog, 
 
 // K(x_i, x_j).  xi / xj point at dimension 0 of the staged inputs; consecutive dimensions are
 // `stride` doubles apart.
-__device__ __forceinline__ double eval_K(const ProgSmem& P, const double* xi, const double* xj, int stride) {
+__device__ __noinline__ double eval_K(const ProgSmem& P, const double* xi, const double* xj, int stride) {
   double val[MAX_TOKENS];
   const int nt = P.ntok;
   for (int t = 0; t < nt; t++) {
@@ -76,7 +78,7 @@ __device__ __forceinline__ double eval_K(const ProgSmem& P, const double* xi, co
 
 // Forward + reverse sweep for one pair: acc[p] += w * dK/dtheta_p for every kernel parameter.
 // `w` is the (already symmetry-weighted) dL/dK entry.
-__device__ __forceinline__ void eval_grad(const ProgSmem& P, const double* xi, const double* xj, int stride, double w,
+__device__ __noinline__ void eval_grad(const ProgSmem& P, const double* xi, const double* xj, int stride, double w,
                                           double* acc, int quirks) {
   double val[MAX_TOKENS], adj[MAX_TOKENS], ax0[MAX_TOKENS], ax1[MAX_TOKENS];
   const int nt = P.ntok;
@@ -87,7 +89,7 @@ __device__ __forceinline__ void eval_grad(const ProgSmem& P, const double* xi, c
       const double a = xi[k.y * stride], b = xj[k.y * stride];
       const double c0 = P.cst[t][0], c1 = P.cst[t][1];
       switch (k.x) {
-        case OP_SE: { double r = (a - b) * c1; a0 = r * r; v = c0 * exp(-0.5 * a0); break; }
+        case OP_SE: { double r = (a - b) * c1; a0 = r * r; a1 = exp(-0.5 * a0); v = c0 * a1; break; }
         case OP_RQ: { double r = (a - b) * c1; double u = (r * r) * P.cst[t][3]; a0 = log1p(u); a1 = u; v = c0 * exp(-P.cst[t][2] * a0); break; }
         case OP_PER: { double s, c; sincos((a - b) * c1, &s, &c); a0 = s; a1 = c; double q = s * P.cst[t][2]; v = c0 * exp(-2.0 * (q * q)); break; }
         case OP_LIN: { a0 = a - c1; a1 = b - c1; v = c0 * (a0 * a1); break; }
@@ -113,13 +115,13 @@ __device__ __forceinline__ void eval_grad(const ProgSmem& P, const double* xi, c
       double* o = acc + k.z;
       switch (k.x) {
         case OP_SE:     // dK/dv = K/v ; dK/dl = K r^2 / l   (stationary.py update_gradients_full)
-          o[0] += g * (v / c0);
+          o[0] += g * ax1[t];
           o[1] += g * (v * ax0[t] * c1);
           break;
         case OP_RQ: {   // rational-quadratic.ipynb#2
           const double e1 = 1.0 / (1.0 + ax1[t]);           // (1 + r^2/2a)^-1
           const double r2 = ax1[t] * (2.0 * P.cst[t][2]);    // r^2
-          o[0] += g * (v / c0);
+          o[0] += g * (v * P.ivar[t]);
           o[1] += g * (v * r2 * c1 * e1);
           o[2] += g * (v * (ax1[t] * e1 - ax0[t]));
           break;
@@ -128,7 +130,7 @@ __device__ __forceinline__ void eval_grad(const ProgSmem& P, const double* xi, c
           const double s = ax0[t], c = ax1[t], il = P.cst[t][2], ip = P.cst[t][3];
           const double base = (xi[k.y * stride] - xj[k.y * stride]) * c1;
           const double q = s * il;
-          o[0] += g * (v / c0);
+          o[0] += g * (v * P.ivar[t]);
           o[1] += g * (v * (4.0 * il * il) * s * c * (base * ip));
           o[2] += g * (v * ((quirks & QUIRK_PER_LENGTHSCALE) ? 1.0 : 4.0) * (q * q) * il);
           break;

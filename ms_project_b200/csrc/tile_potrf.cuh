@@ -23,6 +23,7 @@ constexpr int TP_R = 8;   // elements per thread per dimension (16 * 8 = 128)
 struct TilePotrfSmem {
   double colbuf[2][NB];   // double-buffered pivot column / inverse row
   double piv[NB];         // pivots a_jj (= L_jj^2)
+  double ipiv[2];         // double-buffered reciprocal of the current pivot
   int fail;               // 1-based index of the first non-positive / non-finite pivot
 };
 
@@ -30,6 +31,7 @@ struct TilePotrfSmem {
 // S.piv[j] keeps the pivots (= L_jj^2) for the caller's log-determinant.  S.fail != 0 => not PD.
 __device__ __forceinline__ void tile_potrf(double (&a)[TP_R][TP_R], TilePotrfSmem& S) {
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const bool tyge = ty >= tx;          // i >= c inside a diagonal register block (p == q)
   if (threadIdx.x == 0) S.fail = 0;
 #pragma unroll
   for (int jb = 0; jb < TP_R; jb++) {
@@ -39,23 +41,35 @@ __device__ __forceinline__ void tile_potrf(double (&a)[TP_R][TP_R], TilePotrfSme
       if (tx == jj) {
 #pragma unroll
         for (int p = jb; p < TP_R; p++) cb[ty + 16 * p] = a[p][jb];
+        if (ty == jj) {                 // pivot owner: reciprocal off everybody else's critical path
+          const double piv = a[jb][jb];
+          S.piv[j] = piv;
+          S.ipiv[j & 1] = 1.0 / piv;
+          if (!(piv > 0.0) || !(piv < 1.7e308)) { if (S.fail == 0) S.fail = j + 1; }
+        }
       }
       __syncthreads();
-      const double piv = cb[j];
-      if (threadIdx.x == 0) {
-        S.piv[j] = piv;
-        if (!(piv > 0.0) || !(piv < 1.7e308)) { if (S.fail == 0) S.fail = j + 1; }
-      }
-      const double inv = 1.0 / piv;
+      const double inv = S.ipiv[j & 1];
+      const bool txgt = tx > jj;        // c > j inside the boundary block column (q == jb)
       double rowv[TP_R], colv[TP_R];
 #pragma unroll
       for (int p = jb; p < TP_R; p++) { rowv[p] = cb[ty + 16 * p]; colv[p] = cb[tx + 16 * p] * inv; }
+      // a_ic -= a_ij a_cj / a_jj over j < c <= i.  Register blocks strictly inside the trailing lower
+      // triangle (jb < q < p) need no predicate; only the block column q == jb and the diagonal
+      // blocks p == q do (all block indices are compile-time after unrolling).
 #pragma unroll
       for (int p = jb; p < TP_R; p++) {
 #pragma unroll
-        for (int q = jb; q < TP_R; q++) {
-          const int i = ty + 16 * p, c = tx + 16 * q;
-          if (q <= p && c > j && i >= c) a[p][q] = fma(-rowv[p], colv[q], a[p][q]);
+        for (int q = jb; q <= p; q++) {
+          if (q > jb && q < p) {
+            a[p][q] = fma(-rowv[p], colv[q], a[p][q]);
+          } else {
+            bool ok = true;
+            if (q == jb) ok = ok && txgt;
+            if (p == q) ok = ok && tyge;
+            if (p == jb) ok = ok && (ty > jj);    // rows of block jb at or above the pivot row are dead
+            if (ok) a[p][q] = fma(-rowv[p], colv[q], a[p][q]);
+          }
         }
       }
     }
@@ -65,10 +79,11 @@ __device__ __forceinline__ void tile_potrf(double (&a)[TP_R][TP_R], TilePotrfSme
   for (int q = 0; q < TP_R; q++) {
     const int c = tx + 16 * q;
     const double d = sqrt(S.piv[c]);
+    const double rd = 1.0 / d;          // LAPACK dpotf2 scales the column by 1/ajj as well
 #pragma unroll
-    for (int p = 0; p < TP_R; p++) {
+    for (int p = q; p < TP_R; p++) {
       const int i = ty + 16 * p;
-      if (i > c) a[p][q] = a[p][q] / d;
+      if (i > c) a[p][q] = a[p][q] * rd;
       else if (i == c) a[p][q] = d;
     }
   }
@@ -88,15 +103,17 @@ __device__ __forceinline__ void tile_trtri(double (&d)[TP_R][TP_R], const double
       const int j = jb * 16 + jj;
       double* rb = S.colbuf[j & 1];
       if (ty == jj) {   // owners of row j finish it: D_jc = R_jc / L_jj, and publish it
-        const double ljj = Lsm[j * ldl + j];
+        const double rl = 1.0 / Lsm[j * ldl + j];
 #pragma unroll
         for (int q = 0; q <= jb; q++) {
-          const double v = d[jb][q] / ljj;
+          const double v = d[jb][q] * rl;
           d[jb][q] = v;
           rb[tx + 16 * q] = v;
         }
       }
       __syncthreads();
+      const bool tygt = ty > jj;        // i > j inside block row p == jb
+      const bool txle = tx <= jj;       // c <= j inside block column q == jb
       double lcol[TP_R], rowv[TP_R];
 #pragma unroll
       for (int p = jb; p < TP_R; p++) lcol[p] = Lsm[(ty + 16 * p) * ldl + j];
@@ -106,8 +123,14 @@ __device__ __forceinline__ void tile_trtri(double (&d)[TP_R][TP_R], const double
       for (int p = jb; p < TP_R; p++) {
 #pragma unroll
         for (int q = 0; q <= jb; q++) {
-          const int i = ty + 16 * p, c = tx + 16 * q;
-          if (i > j && c <= j) d[p][q] = fma(-lcol[p], rowv[q], d[p][q]);
+          if (p > jb && q < jb) {
+            d[p][q] = fma(-lcol[p], rowv[q], d[p][q]);
+          } else {
+            bool ok = true;
+            if (p == jb) ok = ok && tygt;
+            if (q == jb) ok = ok && txle;
+            if (ok) d[p][q] = fma(-lcol[p], rowv[q], d[p][q]);
+          }
         }
       }
     }

@@ -37,7 +37,7 @@ class Engine(object):
         self.max_params = 0
         self._ws = None
         self._X = self._y = None
-        self._X_host = None
+        self._X_host = self._y_host = None
 
     def close(self):
         if getattr(self, 'ctx', None):
@@ -59,9 +59,11 @@ class Engine(object):
         n = self.lib.b200gp_last_phase_ms(self.ctx, buf, 8)
         return [float(buf[i]) for i in range(max(n, 0))]
 
-    def slots_for(self, N, D, n_items, max_params, mem_fraction=0.8):
-        """Largest batch the free HBM holds (180 GB / GPU on B200), capped at the number of items."""
+    def slots_for(self, N, D, n_items, max_params, mem_fraction=0.8, extra_bytes=0):
+        """Largest batch the free HBM holds (180 GB / GPU on B200), capped at the number of items.
+        `extra_bytes` counts memory that will be released before the new workspace is allocated."""
         free, _total = self.torch.cuda.mem_get_info(self.device)
+        free += int(extra_bytes)
         per_slot = self.lib.b200gp_workspace_bytes(N, D, 2, max_params) - self.lib.b200gp_workspace_bytes(N, D, 1, max_params)
         fixed = self.lib.b200gp_workspace_bytes(N, D, 1, max_params) - per_slot
         budget = int(free * mem_fraction) - fixed
@@ -83,11 +85,25 @@ class Engine(object):
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self._X = torch.from_numpy(X).to(self.device)
         self._y = torch.from_numpy(y).to(self.device)
-        self._X_host = X
+        self._X_host, self._y_host = X, y
         rc = self.lib.b200gp_bind(self.ctx, self._ws.data_ptr(), self._ws.numel(), int(slots), int(max_params),
                                   self._X.data_ptr(), N, D, self._y.data_ptr())
         _lib.check(self.ctx, rc, 'b200gp_bind')
         self.N, self.D, self.slots, self.max_params = N, D, int(slots), int(max_params)
+
+    def ensure_bound(self, X, y, n_items, max_params):
+        """Bind (X, y) unless the engine already holds the same data with enough slots / parameter room.
+        Slots are sized for `n_items` but capped by the free HBM."""
+        X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+        yv = np.ascontiguousarray(np.asarray(y, dtype=np.float64)).reshape(-1)
+        max_params = max(int(max_params), 1)
+        same = (self._X_host is not None and self._X_host.shape == X.shape and self._y_host.shape == yv.shape
+                and np.array_equal(self._X_host, X) and np.array_equal(self._y_host, yv))
+        want = min(int(n_items), self.slots_for(X.shape[0], X.shape[1], int(n_items), max(max_params, self.max_params),
+                                                extra_bytes=0 if self._ws is None else self._ws.numel()))
+        if same and self.slots >= want and self.max_params >= max_params:
+            return
+        self.bind(X, yv, max(want, 1), max(max_params, self.max_params if same else 1))
 
     # ------------------------------------------------------------------ program staging
     def upload_programs(self, batch):

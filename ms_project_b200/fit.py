@@ -1,0 +1,257 @@
+"""Batched `optimize_restarts`: every (model, restart) pair is an independent L-BFGS-B instance, and all
+instances advance in lock-step against ONE batched LML+gradient launch per iteration.
+
+Replaces the sequential hot loops of the reference:
+  ModelSelector._evaluate_models      src/autoks/core/model_selection/base.py:330   (candidates, one at a time)
+  GPModel.fit -> optimize_restarts    src/autoks/core/gp_model.py:58-82            (restarts, one at a time)
+  paramz Model.optimize / _objective_grads (per function evaluation: GP.parameters_changed)
+while keeping their arithmetic: MAP objective -LML - log p(theta) - log|J| over Logexp-transformed parameters,
+paramz's failure budget, restart draws in the reference's RNG order, argmin over restarts.
+
+Host work per iteration is vectorised over the flat theta layout the device uses; only the compiled
+L-BFGS-B step (scipy's `setulb`) is called per instance."""
+import numpy as np
+
+from .gpy_compat.priors import Gaussian as _GaussianPrior, LogGaussian as _LogGaussianPrior
+from .gpy_compat.transformations import Logexp
+from .optimizer import LBFGSB
+from .program import ProgramBatch
+
+F_MAX = np.finfo(np.float64).max
+ALLOWED_FAILURES = 10          # paramz Model._allowed_failures
+_LOGEXP = Logexp()
+
+
+def check_optimizer(optimizer):
+    """paramz resolves `optimizer=None` to its preferred optimiser, L-BFGS-B, which is what every experiment
+    JSON of the reference uses (training/experiments/*/*.json: "optimizer": null).  Other paramz optimisers
+    (scg, tnc, simplex...) have no batched driver here and are rejected loudly."""
+    if optimizer is None or str(optimizer).lower() in ('lbfgsb', 'lbfgs', 'bfgs', 'l-bfgs-b'):
+        return
+    raise NotImplementedError("optimizer %r: only L-BFGS-B (optimizer=None / 'lbfgsb') is implemented" % (optimizer,))
+
+
+class _PriorTable(object):
+    """Flat per-parameter prior description in device theta layout."""
+
+    def __init__(self, priors):
+        n = len(priors)
+        self.kind = np.zeros(n, dtype=np.int8)     # 0 none, 1 LogGaussian, 2 Gaussian
+        self.mu = np.zeros(n)
+        self.s2 = np.ones(n)
+        self.const = np.zeros(n)
+        for i, p in enumerate(priors):
+            if p is None:
+                continue
+            if type(p) is _LogGaussianPrior:
+                self.kind[i] = 1
+            elif type(p) is _GaussianPrior:
+                self.kind[i] = 2
+            else:
+                raise NotImplementedError('prior %s is not supported on the scoring path' % type(p).__name__)
+            self.mu[i], self.s2[i], self.const[i] = p.mu, p.sigma2, p.constant
+        self.has = self.kind != 0
+        self.lg = self.kind == 1
+        self.ga = self.kind == 2
+
+    def log_prior_terms(self, theta):
+        """Per-parameter lnpdf + log-Jacobian of Logexp (priored parameters only), and their derivatives
+        (GPy priorizable.py log_prior / _log_prior_gradients)."""
+        lp = np.zeros_like(theta)
+        dlp = np.zeros_like(theta)
+        with np.errstate(all='ignore'):
+            if self.lg.any():
+                t = theta[self.lg]
+                lt = np.log(t)
+                lp[self.lg] = self.const[self.lg] - 0.5 * np.square(lt - self.mu[self.lg]) / self.s2[self.lg] - lt
+                dlp[self.lg] = -((lt - self.mu[self.lg]) / self.s2[self.lg] + 1.) / t
+            if self.ga.any():
+                t = theta[self.ga]
+                lp[self.ga] = self.const[self.ga] - 0.5 * np.square(t - self.mu[self.ga]) / self.s2[self.ga]
+                dlp[self.ga] = -(t - self.mu[self.ga]) / self.s2[self.ga]
+            if self.has.any():
+                t = theta[self.has]
+                lp[self.has] += _LOGEXP.log_jacobian(t)
+                dlp[self.has] += _LOGEXP.log_jacobian_grad(t)
+        return lp, dlp
+
+
+class FitResult(object):
+    __slots__ = ('lml', 'status', 'n_evals', 'runs', 'f_opt', 'theta')
+
+    def __init__(self):
+        self.lml = np.nan
+        self.status = 0
+        self.n_evals = 0
+        self.runs = []          # per completed restart: dict(x_opt, f_opt, funcalls, nit, warnflag)
+        self.f_opt = np.nan
+        self.theta = None
+
+
+def _model_priors(kernel, likelihood):
+    return [p.prior for p in kernel.flattened_parameters()] + [p.prior for p in likelihood.flattened_parameters()]
+
+
+def fit_models(engine, kernels, likelihoods, num_restarts=10, max_iters=1000, robust=True, verbose=False,
+               on_iteration=None):
+    """optimize_restarts for M models at once on `engine` (already bound to X, y).
+
+    kernels / likelihoods are modified in place (the optimum is written back, as GPModel.fit does with
+    model.kern / model.likelihood).  Returns a list of FitResult.  Restart r > 0 of model i starts from
+    `randomize()` drawn from the global np.random in the reference's order (model-major, restart-minor)."""
+    M = len(kernels)
+    if M == 0:
+        return []
+    R = int(num_restarts)
+    # ---- starting points, in the reference's RNG order
+    starts = []                     # per instance: constrained parameter vector (kernel params + noise)
+    owner = []                      # instance -> model
+    inst_kernels = []
+    for i, (k, lik) in enumerate(zip(kernels, likelihoods)):
+        cur = np.concatenate([k.param_array, lik.param_array])
+        for r in range(R):
+            if r > 0:
+                cur = _randomized(k, lik)
+            starts.append(cur.copy())
+            owner.append(i)
+            inst_kernels.append(k)
+    owner = np.asarray(owner)
+    n_inst = len(starts)
+    batch = ProgramBatch(inst_kernels)
+    engine.upload_programs(batch)
+    off = batch.theta_off
+    priors = _PriorTable([p for i in range(M) for _ in range(R) for p in _model_priors(kernels[i], likelihoods[i])])
+
+    theta = np.concatenate(starts)
+    x0 = _LOGEXP.finv(theta)
+    opts = [LBFGSB(x0[off[j]:off[j + 1]], maxfun=max_iters, maxiter=max_iters) for j in range(n_inst)]
+    x_all = x0.copy()
+    stale = np.zeros_like(theta)            # last successfully computed dLML/dtheta per instance
+    fail_count = np.zeros(n_inst, dtype=int)
+    aborted = np.zeros(n_inst, dtype=bool)
+    n_evals = np.zeros(n_inst, dtype=int)
+    active = []
+    for j, o in enumerate(opts):
+        x = o.ask()
+        if x is not None:
+            x_all[off[j]:off[j + 1]] = x
+            active.append(j)
+    seg_start = off[:-1]
+    it = 0
+    while active:
+        ids = np.asarray(active, dtype=np.int32)
+        theta = _LOGEXP.f(x_all)
+        lml, dlml, status, _tries = engine.lml_grad(batch, theta, ids=ids, with_grad=True)
+        lp, dlp = priors.log_prior_terms(theta)
+        lp_sum = np.add.reduceat(lp, seg_start)
+        ok = status[ids] != 2                                  # 2 = NOT_PD == GPy raising LinAlgError
+        good = ids[ok]
+        if good.size:
+            mask = _segment_mask(off, good, theta.size)
+            stale[mask] = dlml[mask]
+        g_theta = -(stale + dlp)
+        g_x = _LOGEXP.gradfactor(theta, g_theta)
+        nxt_active = []
+        for j, is_ok in zip(active, ok):
+            a, b = off[j], off[j + 1]
+            n_evals[j] += 1
+            if is_ok:
+                fail_count[j] = 0
+                f, g = -lml[j] - lp_sum[j], g_x[a:b]
+            else:
+                if fail_count[j] >= ALLOWED_FAILURES:          # paramz re-raises: the restart is lost
+                    aborted[j] = True
+                    if not robust:
+                        raise np.linalg.LinAlgError('not positive definite, even with jitter.')
+                    continue
+                fail_count[j] += 1
+                f, g = F_MAX, np.clip(g_x[a:b], -1e10, 1e10)
+            o = opts[j]
+            o.tell(f, g)
+            x = o.ask()
+            if x is not None:
+                x_all[a:b] = x
+                nxt_active.append(j)
+        active = nxt_active
+        it += 1
+        if on_iteration is not None:
+            on_iteration(it, len(active))
+        if verbose:
+            print('lock-step iteration %d: %d / %d instances active' % (it, len(active), n_inst))
+
+    # ---- argmin over each model's completed restarts; write the optimum back
+    results = [FitResult() for _ in range(M)]
+    best_theta = []
+    for i in range(M):
+        res = results[i]
+        best = None
+        for j in np.nonzero(owner == i)[0]:
+            res.n_evals += int(n_evals[j])
+            if aborted[j]:
+                continue
+            run = opts[j].result()
+            run['x_opt'] = run.pop('x')
+            run['f_opt'] = run.pop('f')
+            res.runs.append(run)
+            if best is None or run['f_opt'] < best['f_opt']:
+                best = run
+        if best is not None:
+            th = _LOGEXP.f(best['x_opt'])
+            res.f_opt = best['f_opt']
+        else:                                                   # every restart failed: keep the initial parameters
+            j0 = int(np.nonzero(owner == i)[0][0])
+            th = starts[j0]
+        res.theta = np.asarray(th, dtype=np.float64)
+        best_theta.append(res.theta)
+        kernels[i][:] = res.theta[:-1]
+        likelihoods[i][:] = res.theta[-1:]
+
+    # ---- GP.parameters_changed at the optimum: the model's log_likelihood()
+    final = ProgramBatch(list(kernels))
+    engine.upload_programs(final)
+    th = final.pack_theta([t[:-1] for t in best_theta], [t[-1] for t in best_theta])
+    lml, _g, status, _t = engine.lml_grad(final, th, with_grad=False)
+    for i in range(M):
+        results[i].lml = float(lml[i])
+        results[i].status = int(status[i])
+    return results
+
+
+def _segment_mask(off, items, size):
+    mask = np.zeros(size, dtype=bool)
+    for j in items:
+        mask[off[j]:off[j + 1]] = True
+    return mask
+
+
+def _randomized(kernel, likelihood):
+    """Model-level Priorizable.randomize over [kernel params..., noise]: N(0,1) in optimiser space for every
+    parameter first (one draw of size P+1), then one rvs(count) per distinct prior in order of first
+    appearance."""
+    params = kernel.flattened_parameters() + likelihood.flattened_parameters()
+    x = np.random.normal(size=len(params))
+    vals = np.asarray(_LOGEXP.f(x), dtype=np.float64).copy()
+    seen = []
+    for p in params:
+        if p.prior is not None and not any(p.prior is q for q in seen):
+            seen.append(p.prior)
+    for pr in seen:
+        ind = [i for i, p in enumerate(params) if p.prior is pr]
+        vals[ind] = pr.rvs(len(ind))
+    return vals
+
+
+def map_objective(engine, kernel, likelihood, xs):
+    """MAP objective and gradient in optimiser space (what paramz `_objective_grads` returns) of ONE model at several
+    optimiser-space points `xs` (n x (P+1)), evaluated in one batch.  The model objects are not modified."""
+    xs = np.atleast_2d(np.asarray(xs, dtype=np.float64))
+    n = xs.shape[0]
+    batch = ProgramBatch([kernel] * n)
+    engine.upload_programs(batch)
+    priors = _PriorTable(_model_priors(kernel, likelihood) * n)
+    theta = _LOGEXP.f(xs.reshape(-1))
+    lml, dlml, status, _ = engine.lml_grad(batch, theta, with_grad=True)
+    lp, dlp = priors.log_prior_terms(theta)
+    f = -lml[:n] - lp.reshape(n, -1).sum(1)
+    g = _LOGEXP.gradfactor(theta, -(dlml[:theta.size] + dlp)).reshape(n, -1)
+    return f.copy(), g.copy(), status[:n].copy()

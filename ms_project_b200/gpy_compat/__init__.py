@@ -5,3 +5,6 @@ present the attributes the reference's backend shim uses and delegate every numb
 from . import kern, priors, transformations  # noqa: F401
 from .kern import Kern, RBF, RationalQuadratic, StandardPeriodic, LinScaleShift, Bias, Add, Prod  # noqa: F401
 from .priors import Prior, Gaussian, LogGaussian  # noqa: F401
+from .likelihoods import Likelihood  # noqa: F401,E402
+from . import likelihoods  # noqa: F401,E402
+from .gp import GP  # noqa: F401,E402

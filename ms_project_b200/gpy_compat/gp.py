@@ -1,0 +1,115 @@
+"""`GPy.core.GP` stand-in: the model object `GPModel.build_model` constructs
+(src/autoks/core/gp_model.py:44-56, RawGPModelType at src/autoks/backend/model.py:10) with the attributes the
+reference reads: `optimize_restarts`, `log_likelihood`, `kern`, `likelihood`, `num_data`,
+`_size_transformed`, `param_array`, `predict`, `set_XY`, `X`, `priors` (gp_model.py:64-80;
+backend/model.py:86-108).  Numbers come from libb200gp; optimisation is the batched lock-step driver in
+ms_project_b200.fit run with a batch of one."""
+import numpy as np
+
+from .likelihoods import Gaussian
+from .param import Parameterized
+
+
+class GP(Parameterized):
+    def __init__(self, X, Y, kernel, likelihood=None, mean_function=None, inference_method=None, name='gp',
+                 Y_metadata=None, normalizer=False, device=0):
+        super(GP, self).__init__(name)
+        if mean_function is not None or normalizer:
+            raise NotImplementedError('mean functions / normalisers are outside the scoring path')
+        X = np.asarray(X, dtype=np.float64)
+        Y = np.asarray(Y, dtype=np.float64)
+        assert X.ndim == 2, 'X must be N x D'
+        if Y.ndim == 1:
+            Y = Y[:, None]
+        assert Y.shape == (X.shape[0], 1), 'the scoring path is single-output GP regression (Y is N x 1)'
+        self.X, self.Y = X, Y
+        self.num_data, self.input_dim = X.shape
+        self.kern = kernel
+        self.likelihood = Gaussian() if likelihood is None else likelihood
+        # 'laplace' is accepted because the experiment JSONs pass it; with a Gaussian likelihood its mode is
+        # the exact posterior, and the exact path is what the library implements.
+        self.inference_method = inference_method
+        self.link_parameters(self.kern, self.likelihood)
+        self.optimization_runs = []
+        self._device = device
+        self._lml = None
+        self._status = 0
+
+    # ------------------------------------------------------------------ device evaluation
+    def _engine(self):
+        from ..engine import get_engine
+        return get_engine(self._device)
+
+    def _evaluate(self, with_grad=True):
+        from ..program import ProgramBatch
+        eng = self._engine()
+        batch = ProgramBatch([self.kern])
+        eng.ensure_bound(self.X, self.Y, 1, batch.max_params)
+        eng.upload_programs(batch)
+        theta = batch.pack_theta([self.kern.param_array], [float(self.likelihood.variance)])
+        lml, dlml, status, _ = eng.lml_grad(batch, theta, with_grad=with_grad)
+        self._lml, self._status = float(lml[0]), int(status[0])
+        if with_grad:
+            for p, g in zip(self.flattened_parameters(), dlml[:self.size]):
+                p.gradient[0] = g
+        return self._lml
+
+    def parameters_changed(self):
+        self._lml = None
+
+    def __setitem__(self, item, value):
+        super(GP, self).__setitem__(item, value)
+        self._lml = None
+
+    def log_likelihood(self):
+        """GP.log_likelihood(): the log marginal likelihood at the current parameters."""
+        if self._lml is None:
+            self._evaluate(with_grad=True)
+        if self._status == 2:
+            return np.nan
+        return self._lml
+
+    def log_prior(self):
+        from ..fit import _PriorTable
+        t = _PriorTable([p.prior for p in self.flattened_parameters()])
+        return float(np.sum(t.log_prior_terms(self.param_array)[0]))
+
+    def objective_function(self):
+        return -float(self.log_likelihood()) - self.log_prior()
+
+    # ------------------------------------------------------------------ optimisation
+    @property
+    def optimizer_array(self):
+        return np.array([float(p.constraint.finv(float(p))) for p in self.flattened_parameters()])
+
+    def randomize(self, rand_gen=None, *args, **kwargs):
+        super(GP, self).randomize(rand_gen, *args, **kwargs)
+        self._lml = None
+
+    def optimize(self, optimizer=None, start=None, messages=False, max_iters=1000, ipython_notebook=True,
+                 clear_after_finish=False, **kwargs):
+        return self.optimize_restarts(num_restarts=1, optimizer=optimizer, max_iters=max_iters, verbose=False)
+
+    def optimize_restarts(self, num_restarts=10, robust=False, verbose=True, parallel=False, num_processes=None,
+                          optimizer=None, max_iters=1000, ipython_notebook=False, messages=False, **kwargs):
+        from ..fit import fit_models, check_optimizer
+        check_optimizer(optimizer)
+        eng = self._engine()
+        eng.ensure_bound(self.X, self.Y, max(int(num_restarts), 1), self.kern.size)
+        res = fit_models(eng, [self.kern], [self.likelihood], num_restarts=num_restarts, max_iters=max_iters,
+                         robust=robust)[0]
+        self.optimization_runs += res.runs
+        self._lml, self._status = res.lml, res.status
+        return self.optimization_runs
+
+    def set_XY(self, X=None, Y=None):
+        if X is not None:
+            self.X = np.asarray(X, dtype=np.float64)
+            self.num_data = self.X.shape[0]
+        if Y is not None:
+            self.Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)
+        self._lml = None
+
+    def predict(self, Xnew, full_cov=False, Y_metadata=None, kern=None, likelihood=None, include_likelihood=True):
+        from ..posterior import predict as _predict
+        return _predict(self, Xnew, full_cov=full_cov, include_likelihood=include_likelihood)
