@@ -86,6 +86,24 @@ int b200gp_lml_grad(b200gp_ctx* ctx, const int32_t* d_prog, const int32_t* d_pro
 size_t b200gp_potrf_work_bytes(int N);
 int b200gp_potrf(b200gp_ctx* ctx, double* d_A, int N, void* d_work, double* logdet, int32_t* status);
 
+/* ---- BOMS Hellinger kernel-kernel distance (src/autoks/distance/distance.py:126-194) ------------------------
+ * precompute: for model m (program m, P_m kernel parameters) and sample s: G = K(theta[m][s]) + lambda[s] I over the
+ *   n-point subset d_Xsub (n x D row-major, n <= 128), d_logdet[m*S+s] = log det G, optional d_G[m][s] = G (n x n dense).
+ *   d_theta_samples is packed [model][sample][param]: model m starts at theta_off[m]*S doubles (theta_off counts
+ *   kernel parameters only -- there is no noise entry here; lambda plays that role).  status 1 = not PD.
+ *   (create_precomputed_info, distance.py:170-194)
+ * pairs: d_dist[p] = Hellinger distance of models (pair_i[p], pair_j[p]); samples whose logdets differ by <= tol_logdet
+ *   re-use logdet_i (distance.py:145-148).  status 1 = a 1/2(G_i+G_j) was not PD (the reference would call
+ *   cov_nearest there); d_work needs b200gp_hellinger_pairs_work_bytes(npairs, S).
+ *   (hellinger_distance + compute_distance, distance.py:135-168,110-118) */
+int b200gp_hellinger_precompute(b200gp_ctx* ctx, const double* d_Xsub, int n, int D, const int32_t* d_prog,
+                                const int32_t* d_prog_off, const double* d_theta_samples, const int32_t* d_theta_off,
+                                const double* d_lambda, int M, int S, double* d_logdet, double* d_G, int32_t* d_status);
+size_t b200gp_hellinger_pairs_work_bytes(int npairs, int S);
+int b200gp_hellinger_pairs(b200gp_ctx* ctx, const double* d_logdet, const double* d_G, int M, int S, int n,
+                           const int32_t* d_pair_i, const int32_t* d_pair_j, int npairs, double tol_logdet, void* d_work,
+                           double* d_dist, int32_t* d_status);
+
 /* Phase timings (ms) of the most recent b200gp_lml_grad chunk, measured with CUDA events on the context
  * stream: [build_K, cholesky, inverse(V), solve, Kinv, grad+finalize].  Returns the number written. */
 int b200gp_last_phase_ms(b200gp_ctx* ctx, float* out, int cap);

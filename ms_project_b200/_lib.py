@@ -59,24 +59,19 @@ def _declare(lib):
     lib.b200gp_potrf_work_bytes.argtypes = [ctypes.c_int]
     lib.b200gp_potrf.restype = ctypes.c_int
     lib.b200gp_potrf.argtypes = [vp, vp, ctypes.c_int, vp, c_double_p, c_int_p]
-    for name, args in _OPTIONAL.items():
-        if hasattr(lib, name):
-            fn = getattr(lib, name)
-            fn.restype = ctypes.c_int
-            fn.argtypes = args
-
-
-_vp = ctypes.c_void_p
-_OPTIONAL = {
-    'b200gp_hellinger_precompute': [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, ctypes.c_int,
-                                    ctypes.c_int, _vp, _vp, _vp],
-    'b200gp_hellinger_pairs': [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int,
-                               ctypes.c_double, _vp, _vp],
-}
+    lib.b200gp_hellinger_precompute.restype = ctypes.c_int
+    lib.b200gp_hellinger_precompute.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int,
+                                                ctypes.c_int, vp, vp, vp]
+    lib.b200gp_hellinger_pairs_work_bytes.restype = ctypes.c_size_t
+    lib.b200gp_hellinger_pairs_work_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.b200gp_hellinger_pairs.restype = ctypes.c_int
+    lib.b200gp_hellinger_pairs.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int,
+                                           ctypes.c_double, vp, vp, vp]
 
 EXPORTS = ['b200gp_version', 'b200gp_create', 'b200gp_destroy', 'b200gp_last_error', 'b200gp_set_quirks',
            'b200gp_set_profiling', 'b200gp_launch_count', 'b200gp_last_phase_ms', 'b200gp_workspace_bytes',
-           'b200gp_bind', 'b200gp_build_K', 'b200gp_lml_grad', 'b200gp_potrf_work_bytes', 'b200gp_potrf']
+           'b200gp_bind', 'b200gp_build_K', 'b200gp_lml_grad', 'b200gp_potrf_work_bytes', 'b200gp_potrf',
+           'b200gp_hellinger_precompute', 'b200gp_hellinger_pairs_work_bytes', 'b200gp_hellinger_pairs']
 
 
 def lib():

@@ -12,6 +12,12 @@ using namespace b200gp;
 
 namespace b200gp {
 long long g_launch_count = 0;
+int configure_hellinger_kernels();
+void launch_hellinger_precompute(const double* Xsub, int n, int D, const int4* prog, const int* prog_off,
+                                 const double* theta, const int* theta_off, const double* lambda, int M, int S,
+                                 double* logdet, double* G, int* status, cudaStream_t st);
+void launch_hellinger_pairs(const double* logdet, const double* G, int S, int n, const int* pair_i, const int* pair_j,
+                            int npairs, double tol, double* h, int* hstatus, double* dist, int* status, cudaStream_t st);
 void launch_pack_data(const double* X, const double* y, int N, int D, int Np, double* Xt, double* yp, cudaStream_t s);
 }
 
@@ -109,7 +115,7 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -3;
   if (prop.major < 10) return -4;   // sm_100a only: there is no fallback path
-  if (configure_kernels() != 0) return -5;
+  if (configure_kernels() != 0 || configure_hellinger_kernels() != 0) return -5;
   b200gp_ctx* c = new b200gp_ctx();
   c->device = device;
   c->stream = static_cast<cudaStream_t>(cuda_stream);
@@ -376,6 +382,53 @@ int b200gp_potrf(b200gp_ctx* c, double* dA, int N, void* work, double* logdet, i
   *logdet = st == 0 ? ld : NAN;
   *status = st;
   return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int b200gp_hellinger_precompute(b200gp_ctx* c, const double* dXsub, int n, int D, const int32_t* prog,
+                                const int32_t* prog_off, const double* theta_samples, const int32_t* theta_off,
+                                const double* lambda, int M, int S, double* logdet, double* G, int32_t* status) {
+  if (!c) return -1;
+  if (!dXsub || !prog || !prog_off || !theta_samples || !theta_off || !lambda || !logdet || !status)
+    return fail(c, "b200gp_hellinger_precompute: null pointer");
+  if (n <= 0 || n > NB) return fail(c, "b200gp_hellinger_precompute: subset size must be in [1, %d]", NB);
+  if (D <= 0 || D > MAX_DIMS) return fail(c, "b200gp_hellinger_precompute: need 0 < D <= %d", MAX_DIMS);
+  if (M <= 0 || S <= 0 || S > 65535) return fail(c, "b200gp_hellinger_precompute: bad M / S");
+  CUCHECK(c, cudaSetDevice(c->device));
+  for (int off = 0; off < M; off += 32768) {     // grid.y limit
+    const int m = M - off < 32768 ? M - off : 32768;
+    // prog_off / theta_off are absolute, so a chunk only shifts the model index base
+    launch_hellinger_precompute(dXsub, n, D, reinterpret_cast<const int4*>(prog), prog_off + off, theta_samples,
+                                theta_off + off, lambda, m, S, logdet + (size_t)off * S,
+                                G ? G + (size_t)off * S * n * n : nullptr, status + (size_t)off * S, c->stream);
+  }
+  CUCHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int b200gp_hellinger_pairs(b200gp_ctx* c, const double* logdet, const double* G, int M, int S, int n,
+                           const int32_t* pair_i, const int32_t* pair_j, int npairs, double tol_logdet, void* work,
+                           double* dist, int32_t* status) {
+  if (!c) return -1;
+  if (!logdet || !G || !pair_i || !pair_j || !dist || !status || !work)
+    return fail(c, "b200gp_hellinger_pairs: null pointer");
+  if (n <= 0 || n > NB || M <= 0 || S <= 0 || S > 65535) return fail(c, "b200gp_hellinger_pairs: bad geometry");
+  if (npairs <= 0) return 0;
+  CUCHECK(c, cudaSetDevice(c->device));
+  Carver cv(work);
+  double* h = cv.take<double>((size_t)npairs * S);
+  int* hs = cv.take<int>((size_t)npairs * S);
+  launch_hellinger_pairs(logdet, G, S, n, pair_i, pair_j, npairs, tol_logdet, h, hs, dist, status, c->stream);
+  CUCHECK(c, cudaGetLastError());
+  return 0;
+}
+
+size_t b200gp_hellinger_pairs_work_bytes(int npairs, int S) {
+  if (npairs <= 0 || S <= 0) return 0;
+  return (size_t)npairs * S * (sizeof(double) + sizeof(int)) + 1024;
 }
 
 }  // extern "C"

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) potrf_diag_kernel(Batch b, int 
 #pragma unroll
     for (int q = 0; q < TP_R; q++) a[p][q] = A[(size_t)(ty + 16 * p) * b.Np + tx + 16 * q];
 
-  tile_potrf(a, S);
+  tile_potrf<true>(a, S, NB);
   if (S.fail != 0) {   // uniform: S.fail was written before the last barrier inside tile_potrf
     if (threadIdx.x == 0) b.slot_status[slot] = k * NB + S.fail;
     return;

@@ -20,17 +20,15 @@ struct ProgSmem {
 };
 
 // Cooperative load of item `item`'s program + theta into shared memory; derives leaf constants.
-__device__ inline void load_program(ProgSmem& P, const int4* __restrict__ prog, const int* __restrict__ prog_off,
-                                    const double* __restrict__ theta, const int* __restrict__ theta_off, int item) {
-  const int t0 = prog_off[item], t1 = prog_off[item + 1];
-  const int th0 = theta_off[item];
-  const int nt = t1 - t0;
+// `th_base` points at the item's first kernel parameter; `noise` is its Gaussian noise variance.
+__device__ inline void load_program_at(ProgSmem& P, const int4* __restrict__ toks, int nt,
+                                       const double* __restrict__ th_base, int nparam, double noise) {
   for (int t = threadIdx.x; t < nt; t += blockDim.x) {
-    int4 k = prog[t0 + t];
+    int4 k = toks[t];
     P.tok[t] = k;
     double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     if (k.x <= OP_CONST) {
-      const double* th = theta + th0 + k.z;
+      const double* th = th_base + k.z;
       switch (k.x) {
         case OP_SE:  c0 = th[0]; c1 = 1.0 / th[1]; break;                                   // [variance, lengthscale]
         case OP_RQ:  c0 = th[0]; c1 = 1.0 / th[1]; c2 = th[2]; c3 = 1.0 / (2.0 * th[2]); break;  // [.., power]
@@ -44,14 +42,20 @@ __device__ inline void load_program(ProgSmem& P, const int4* __restrict__ prog, 
   }
   if (threadIdx.x == 0) {
     P.ntok = nt;
-    P.nparam = theta_off[item + 1] - th0 - 1;
-    P.noise = theta[theta_off[item + 1] - 1];
+    P.nparam = nparam;
+    P.noise = noise;
   }
+}
+
+__device__ inline void load_program(ProgSmem& P, const int4* __restrict__ prog, const int* __restrict__ prog_off,
+                                    const double* __restrict__ theta, const int* __restrict__ theta_off, int item) {
+  const int t0 = prog_off[item], th0 = theta_off[item], th1 = theta_off[item + 1];
+  load_program_at(P, prog + t0, prog_off[item + 1] - t0, theta + th0, th1 - th0 - 1, theta[th1 - 1]);
 }
 
 // K(x_i, x_j).  xi / xj point at dimension 0 of the staged inputs; consecutive dimensions are
 // `stride` doubles apart.
-__device__ __noinline__ double eval_K(const ProgSmem& P, const double* xi, const double* xj, int stride) {
+static __device__ __noinline__ double eval_K(const ProgSmem& P, const double* xi, const double* xj, int stride) {
   double val[MAX_TOKENS];
   const int nt = P.ntok;
   for (int t = 0; t < nt; t++) {
@@ -78,7 +82,7 @@ __device__ __noinline__ double eval_K(const ProgSmem& P, const double* xi, const
 
 // Forward + reverse sweep for one pair: acc[p] += w * dK/dtheta_p for every kernel parameter.
 // `w` is the (already symmetry-weighted) dL/dK entry.
-__device__ __noinline__ void eval_grad(const ProgSmem& P, const double* xi, const double* xj, int stride, double w,
+static __device__ __noinline__ void eval_grad(const ProgSmem& P, const double* xi, const double* xj, int stride, double w,
                                           double* acc, int quirks) {
   double val[MAX_TOKENS], adj[MAX_TOKENS], ax0[MAX_TOKENS], ax1[MAX_TOKENS];
   const int nt = P.ntok;

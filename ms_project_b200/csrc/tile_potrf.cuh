@@ -29,14 +29,22 @@ struct TilePotrfSmem {
 
 // Phase 1.  On exit a[p][q] holds L (lower, i >= c); entries above the diagonal are junk.
 // S.piv[j] keeps the pivots (= L_jj^2) for the caller's log-determinant.  S.fail != 0 => not PD.
-__device__ __forceinline__ void tile_potrf(double (&a)[TP_R][TP_R], TilePotrfSmem& S) {
+// `nact` (<= NB) is the order of the active leading block: rows / columns >= nact are identity padding and
+// their elimination steps are skipped (their pivots read as 1).  kScale = false leaves the columns unscaled
+// (enough when only the log-determinant is wanted).
+template <bool kScale>
+__device__ __forceinline__ void tile_potrf(double (&a)[TP_R][TP_R], TilePotrfSmem& S, int nact) {
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   const bool tyge = ty >= tx;          // i >= c inside a diagonal register block (p == q)
   if (threadIdx.x == 0) S.fail = 0;
+  if (threadIdx.x < NB) S.piv[threadIdx.x] = 1.0;
+  __syncthreads();
 #pragma unroll
   for (int jb = 0; jb < TP_R; jb++) {
+    if (jb * 16 >= nact) break;
     for (int jj = 0; jj < 16; jj++) {
       const int j = jb * 16 + jj;
+      if (j >= nact) break;
       double* cb = S.colbuf[j & 1];
       if (tx == jj) {
 #pragma unroll
@@ -75,6 +83,7 @@ __device__ __forceinline__ void tile_potrf(double (&a)[TP_R][TP_R], TilePotrfSme
     }
   }
   __syncthreads();
+  if (!kScale) return;
 #pragma unroll
   for (int q = 0; q < TP_R; q++) {
     const int c = tx + 16 * q;
