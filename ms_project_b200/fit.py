@@ -92,8 +92,22 @@ def _model_priors(kernel, likelihood):
     return [p.prior for p in kernel.flattened_parameters()] + [p.prior for p in likelihood.flattened_parameters()]
 
 
+def draw_starts(kernels, likelihoods, num_restarts):
+    """Starting points of every (model, restart) instance in the reference's RNG order (model-major,
+    restart-minor): restart 0 = the model's current parameters, restart r > 0 = `randomize()` from the global
+    np.random.  Returns a list (per model) of lists (per restart) of constrained parameter vectors."""
+    out = []
+    for k, lik in zip(kernels, likelihoods):
+        cur = np.concatenate([k.param_array, lik.param_array])
+        mine = [cur.copy()]
+        for _ in range(1, int(num_restarts)):
+            mine.append(_randomized(k, lik))
+        out.append(mine)
+    return out
+
+
 def fit_models(engine, kernels, likelihoods, num_restarts=10, max_iters=1000, robust=True, verbose=False,
-               on_iteration=None):
+               on_iteration=None, starts=None):
     """optimize_restarts for M models at once on `engine` (already bound to X, y).
 
     kernels / likelihoods are modified in place (the optimum is written back, as GPModel.fit does with
@@ -103,16 +117,15 @@ def fit_models(engine, kernels, likelihoods, num_restarts=10, max_iters=1000, ro
     if M == 0:
         return []
     R = int(num_restarts)
-    # ---- starting points, in the reference's RNG order
+    # ---- starting points, in the reference's RNG order (or pre-drawn by the caller, e.g. a sharded run)
+    per_model = draw_starts(kernels, likelihoods, R) if starts is None else starts
     starts = []                     # per instance: constrained parameter vector (kernel params + noise)
     owner = []                      # instance -> model
     inst_kernels = []
-    for i, (k, lik) in enumerate(zip(kernels, likelihoods)):
-        cur = np.concatenate([k.param_array, lik.param_array])
+    for i, k in enumerate(kernels):
+        assert len(per_model[i]) == R
         for r in range(R):
-            if r > 0:
-                cur = _randomized(k, lik)
-            starts.append(cur.copy())
+            starts.append(np.asarray(per_model[i][r], dtype=np.float64))
             owner.append(i)
             inst_kernels.append(k)
     owner = np.asarray(owner)

@@ -113,10 +113,22 @@ def plan_evaluation(models, n_evals, eval_budget, visited, skip_evaluated=True):
     return to_fit, order
 
 
-def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engine=None, model_dict=None):
+def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engine=None, model_dict=None,
+                 all_models=None, shard=None):
     """GPModel.score_model for a whole list in ONE lock-step GPU batch (same per-model results and side effects as
     calling score_model on each, including the retry-once rule and failed_fitting)."""
     check_optimizer(optimizer)
+    if all_models is not None:
+        # sharded run: draw the restart points of the WHOLE list (identical on every rank), keep our slice
+        all_gps = []
+        for m in all_models:
+            _prepare(m, model_dict)
+            all_gps.append(m.build_model(x, y))
+        from .fit import draw_starts
+        starts_all = draw_starts([g.kern for g in all_gps], [g.likelihood for g in all_gps], n_restarts)
+        starts = starts_all[shard[0]:shard[1]]
+    else:
+        starts = None
     if not models:
         return []
     if engine is None:
@@ -124,14 +136,12 @@ def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engi
         engine = get_engine(0)
     gps = []
     for m in models:
-        if model_dict:
-            m.model_input_dict = {k: copy.deepcopy(v) for k, v in model_dict.items() if k != 'likelihood'}
-            if m.likelihood is None and model_dict.get('likelihood') is not None:
-                m.likelihood = model_dict['likelihood'].copy()
+        _prepare(m, model_dict)
         gps.append(m.build_model(x, y))
     maxp = max(g.kern.size for g in gps)
     engine.ensure_bound(x, y, len(gps) * max(int(n_restarts), 1), maxp)
-    results = fit_models(engine, [g.kern for g in gps], [g.likelihood for g in gps], num_restarts=n_restarts, robust=True)
+    results = fit_models(engine, [g.kern for g in gps], [g.likelihood for g in gps], num_restarts=n_restarts, robust=True,
+                         starts=starts)
     for g, r in zip(gps, results):
         g._lml, g._status = r.lml, r.status
         g.optimization_runs += r.runs
@@ -149,6 +159,13 @@ def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engi
         m.fit_result = r
         m.score = scoring_func(g) if not m.failed_fitting else np.nan
     return [m.score for m in models]
+
+
+def _prepare(m, model_dict):
+    if model_dict:
+        m.model_input_dict = {k: copy.deepcopy(v) for k, v in model_dict.items() if k != 'likelihood'}
+        if m.likelihood is None and model_dict.get('likelihood') is not None:
+            m.likelihood = model_dict['likelihood'].copy()
 
 
 class BatchedEvaluator(object):
