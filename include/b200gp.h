@@ -108,6 +108,8 @@ int b200gp_hellinger_pairs(b200gp_ctx* ctx, const double* d_logdet, const double
  * stream: [build_K, cholesky, inverse(V), solve, Kinv, grad+finalize].  Returns the number written. */
 int b200gp_last_phase_ms(b200gp_ctx* ctx, float* out, int cap);
 int b200gp_set_profiling(b200gp_ctx* ctx, int enabled);
+/* panel width (in 128-column tiles) of the look-ahead Cholesky used for single large matrices; default 2 */
+int b200gp_set_panel_tiles(b200gp_ctx* ctx, int tiles);
 /* kernels launched by this context since creation (for bench.py's gpu_launches) */
 long long b200gp_launch_count(b200gp_ctx* ctx);
 

@@ -30,6 +30,8 @@ struct b200gp_ctx {
   bool profiling = false;
   Batch base{};             // geometry + workspace pointers
   int slots = 0, max_params = 0;
+  int panel_tiles = 4;          // look-ahead Cholesky (single large matrix)
+  int batch_panel_tiles = 4;    // batched Cholesky
   double* ws_jitter = nullptr;
   int* ws_ids = nullptr;
   int* ws_tries_dummy = nullptr;
@@ -40,6 +42,8 @@ struct b200gp_ctx {
   double* h_jit = nullptr;
   size_t h_cap = 0;
   cudaEvent_t ev[8]{};
+  cudaStream_t side = nullptr;     // high-priority stream for the look-ahead panel of large single factorisations
+  cudaEvent_t evP = nullptr, evR = nullptr, evS = nullptr;
   float phase_ms[6]{};
   int n_phase = 0;
 };
@@ -120,6 +124,12 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
   c->device = device;
   c->stream = static_cast<cudaStream_t>(cuda_stream);
   for (auto& e : c->ev) cudaEventCreate(&e);
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi);
+  cudaEventCreateWithFlags(&c->evP, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->evR, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->evS, cudaEventDisableTiming);
   *out = c;
   return 0;
 }
@@ -128,6 +138,8 @@ int b200gp_destroy(b200gp_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   for (auto& e : c->ev) cudaEventDestroy(e);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->evP) { cudaEventDestroy(c->evP); cudaEventDestroy(c->evR); cudaEventDestroy(c->evS); }
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->h_ids) cudaFreeHost(c->h_ids);
   if (c->h_diag) cudaFreeHost(c->h_diag);
@@ -141,6 +153,13 @@ const char* b200gp_last_error(b200gp_ctx* c) { return c ? c->err.c_str() : "null
 int b200gp_set_quirks(b200gp_ctx* c, int mask) {
   if (!c) return -1;
   c->quirks = mask;
+  return 0;
+}
+
+int b200gp_set_panel_tiles(b200gp_ctx* c, int tiles) {
+  if (!c || tiles < 1 || tiles > 16) return -1;
+  c->panel_tiles = tiles;
+  c->batch_panel_tiles = tiles;
   return 0;
 }
 
@@ -206,6 +225,42 @@ int b200gp_bind(b200gp_ctx* c, void* ws, size_t ws_bytes, int slots, int max_par
 
 }  // extern "C"
 
+// Right-looking blocked Cholesky of every slot of `b` (M1 in place).
+//  * many slots: plain step loop -- the batch itself fills the GPU;
+//  * few slots (a single large matrix): one-step look-ahead.  The next panel (update of column k+1, its diagonal
+//    factorisation and its TRSM) runs on a high-priority side stream while the main stream is still applying
+//    step k to the rest of the trailing matrix, so the latency-bound panel disappears behind the DMMA update.
+static void cholesky_phase(b200gp_ctx* c, const Batch& b) {
+  const int T = b.T;
+  const bool la = (b.nslots < 8 && T >= 8);          // look-ahead on the side stream only pays for few, large matrices
+  cudaStream_t s0 = c->stream, s1 = la ? c->side : c->stream;
+  const int W = la ? c->panel_tiles : c->batch_panel_tiles;   // panel width in tiles: trailing updates run with K = 128 W
+  auto panel = [&](int k0, int k1) {                 // factor tile columns [k0, k1) given everything left of k0 applied
+    for (int k = k0; k < k1; k++) {
+      launch_potrf_diag(b, k, s1);
+      if (k + 1 < T) launch_gemm(b, GM_TRSM, k, s1);
+      if (k + 1 < k1) launch_update(b, UpdRange{k, 1, k + 1, k1}, s1);
+    }
+  };
+  if (la) { cudaEventRecord(c->evS, s0); cudaStreamWaitEvent(s1, c->evS, 0); }
+  panel(0, W < T ? W : T);
+  if (la) cudaEventRecord(c->evP, s1);
+  bool have_r = false;
+  for (int k0 = 0; k0 + W < T; k0 += W) {
+    const int k1 = k0 + W;
+    const int n1 = (k1 + W < T) ? k1 + W : T;        // end of the next panel
+    if (la) cudaStreamWaitEvent(s0, c->evP, 0);              // panel [k0, k1) is factored
+    if (la && have_r) cudaStreamWaitEvent(s1, c->evR, 0);    // columns [k1, n1) have every earlier trailing update
+    launch_update(b, UpdRange{k0, W, k1, n1}, s1);   // look-ahead: the next panel's columns first ...
+    if (n1 < T) launch_update(b, UpdRange{k0, W, n1, T}, s0);   // ... the rest of the trailing matrix meanwhile
+    if (la) cudaEventRecord(c->evR, s0);
+    have_r = true;
+    panel(k1, n1);
+    if (la) cudaEventRecord(c->evP, s1);
+  }
+  if (la) cudaStreamWaitEvent(s0, c->evP, 0);
+}
+
 // Enqueue all phases for one chunk.  Phase events are recorded only when profiling is on.
 static void run_pipeline(b200gp_ctx* c, const Batch& b, int with_grad) {
   cudaStream_t s = c->stream;
@@ -214,13 +269,7 @@ static void run_pipeline(b200gp_ctx* c, const Batch& b, int with_grad) {
   if (prof) cudaEventRecord(c->ev[0], s);
   launch_build_k(b, s);
   if (prof) cudaEventRecord(c->ev[1], s);
-  for (int k = 0; k < b.T; k++) {
-    launch_potrf_diag(b, k, s);
-    if (k + 1 < b.T) {
-      launch_gemm(b, GM_TRSM, k, s);
-      launch_gemm(b, GM_SYRK, k, s);
-    }
-  }
+  cholesky_phase(c, b);
   if (prof) cudaEventRecord(c->ev[2], s);
   for (int i = 1; i < b.T; i++) {
     launch_gemm(b, GM_VACC, i, s);
@@ -362,13 +411,7 @@ int b200gp_potrf(b200gp_ctx* c, double* dA, int N, void* work, double* logdet, i
   cudaStream_t s = c->stream;
   CUCHECK(c, cudaMemsetAsync(b.slot_status, 0, sizeof(int), s));
   if (c->profiling) cudaEventRecord(c->ev[0], s);
-  for (int k = 0; k < T; k++) {
-    launch_potrf_diag(b, k, s);
-    if (k + 1 < T) {
-      launch_gemm(b, GM_TRSM, k, s);
-      launch_gemm(b, GM_SYRK, k, s);
-    }
-  }
+  cholesky_phase(c, b);
   if (c->profiling) cudaEventRecord(c->ev[1], s);
   CUCHECK(c, cudaGetLastError());
   std::vector<double> parts(T);

@@ -94,7 +94,7 @@ void launch_potrf_diag(const Batch& b, int k, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // Tile GEMM phases
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TG_THREADS, 1) gemm_kernel(Batch b, int mode, int step) {
+__global__ void __launch_bounds__(TG_THREADS, 1) gemm_kernel(Batch b, int mode, int step, UpdRange upd) {
   const int slot = blockIdx.y;
   if (b.slot_status[slot] != 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -130,6 +130,25 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_kernel(Batch b, int mode, 
       alpha = -1.0; beta = -1.0;
       break;
     }
+    case GM_UPD: {         // A_ij -= sum_{k in [k0, k0+kw)} L_ik L_jk^T, columns j in [j0, j1)
+      int i, j;
+      if (upd.j1 >= b.T) {
+        int r, c;
+        tri_decode(bx, r, c);
+        i = upd.j0 + r; j = upd.j0 + c;
+      } else {
+        int rem = bx;
+        j = upd.j0;
+        while (rem >= b.T - j) { rem -= b.T - j; j++; }
+        i = j + rem;
+      }
+      C = M1 + (size_t)(i * NB) * ld + j * NB;
+      A = M1 + (size_t)(i * NB) * ld + upd.k0 * NB;
+      B = M1 + (size_t)(j * NB) * ld + upd.k0 * NB;
+      nchunks = upd.kw * (NB / TG_KC);
+      alpha = -1.0; beta = -1.0;
+      break;
+    }
     case GM_VACC: {        // S_ji = sum_{k=j}^{i-1} V_jk L_ik^T  (stored where V_ji will live)
       const int i = step, j = bx;
       C = M2 + (size_t)(j * NB) * ld + i * NB;
@@ -160,32 +179,32 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_kernel(Batch b, int mode, 
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, tg = lane & 3;
-  double* Cw = C + (size_t)(wm * 64 + g) * ld + wn * 32 + tg * 2;
+  const int wm = warp / TG_WN, wn = warp % TG_WN, g = lane >> 2, tg = lane & 3;
+  double* Cw = C + (size_t)(wm * 8 * TG_MT + g) * ld + wn * 8 * TG_NT + tg * 2;
 
-  double acc[8][4][2];
+  double acc[TG_MT][TG_NT][2];
   if (beta != 0.0) {       // accumulators start at beta*C so the C read overlaps the pipeline fill
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++)
+    for (int mt = 0; mt < TG_MT; mt++)
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) {
+      for (int nt = 0; nt < TG_NT; nt++) {
         const double2 v = *reinterpret_cast<const double2*>(Cw + (size_t)(mt * 8) * ld + nt * 8);
         acc[mt][nt][0] = beta * v.x;
         acc[mt][nt][1] = beta * v.y;
       }
   } else {
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++)
+    for (int mt = 0; mt < TG_MT; mt++)
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+      for (int nt = 0; nt < TG_NT; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
   }
 
   tile_gemm_nt(acc, A, ld, B, ldb, nchunks, smem);
 
 #pragma unroll
-  for (int mt = 0; mt < 8; mt++)
+  for (int mt = 0; mt < TG_MT; mt++)
 #pragma unroll
-    for (int nt = 0; nt < 4; nt++) {
+    for (int nt = 0; nt < TG_NT; nt++) {
       double2 v;
       v.x = alpha * acc[mt][nt][0];
       v.y = alpha * acc[mt][nt][1];
@@ -204,7 +223,16 @@ void launch_gemm(const Batch& b, int mode, int step, cudaStream_t s) {
   }
   if (ntiles <= 0) return;
   dim3 grid(ntiles, b.nslots);
-  gemm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, mode, step);
+  gemm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, mode, step, UpdRange{0, 0, 0, 0});
+  g_launch_count++;
+}
+
+void launch_update(const Batch& b, UpdRange r, cudaStream_t s) {
+  int ntiles = 0;
+  for (int j = r.j0; j < r.j1 && j < b.T; j++) ntiles += b.T - j;
+  if (ntiles <= 0 || r.kw <= 0) return;
+  dim3 grid(ntiles, b.nslots);
+  gemm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, GM_UPD, r.k0, r);
   g_launch_count++;
 }
 

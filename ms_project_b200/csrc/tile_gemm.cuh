@@ -4,7 +4,7 @@
 // Cholesky / inverse is arranged (see chol_kernels.cu).  Blackwell's tcgen05/UMMA has no FP64 kind;
 // the FP64 tensor path on sm_100a is `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4, measured 36.9 TFLOP/s
 // register-resident, profiles/fp64_peaks_r01.json), so this is a warp-level MMA kernel:
-//   * 256 threads = 8 warps in a 2 (M) x 4 (N) grid, warp tile 64 x 32 = 8 x 4 DMMA tiles
+//   * TG_WM x TG_WN warps (default 4 x 4 = 512 threads), warp tile (128/TG_WM) x 32 DMMA m8n8 tiles
 //   * operands stream global -> shared through a 4-stage cp.async (LDGSTS) ring, 16 doubles of K
 //     per stage, rows padded to 20 doubles so the 64-bit fragment loads are bank-conflict free
 //   * one __syncthreads per stage
@@ -13,7 +13,14 @@
 
 namespace b200gp {
 
-constexpr int TG_THREADS = 256;
+#ifndef TG_WARPS_M
+#define TG_WARPS_M 4
+#endif
+constexpr int TG_WM = TG_WARPS_M;         // warps along M
+constexpr int TG_WN = 4;                  // warps along N
+constexpr int TG_THREADS = 32 * TG_WM * TG_WN;
+constexpr int TG_MT = NB / TG_WM / 8;     // DMMA m-tiles per warp
+constexpr int TG_NT = NB / TG_WN / 8;     // DMMA n-tiles per warp
 constexpr int TG_KC = 16;                 // K elements per pipeline stage
 constexpr int TG_LDK = TG_KC + 4;         // padded row length in shared memory (doubles)
 constexpr int TG_STAGES = 4;
@@ -39,7 +46,7 @@ __device__ __forceinline__ void tg_load_stage(double* stage, const double* __res
   double* As = stage;
   double* Bs = stage + NB * TG_LDK;
 #pragma unroll
-  for (int r = 0; r < 4; r++) {
+  for (int r = 0; r < 1024 / TG_THREADS; r++) {
     const int seg = threadIdx.x + TG_THREADS * r;   // 1024 16-byte segments per operand
     const int row = seg >> 3, part = (seg & 7) * 2;
     cp_async16(As + row * TG_LDK + part, A + (size_t)row * lda + koff + part);
@@ -47,13 +54,13 @@ __device__ __forceinline__ void tg_load_stage(double* stage, const double* __res
   }
 }
 
-// acc[mt][nt][2]: C fragment of DMMA tile (mt, nt) of this warp's 64x32 sub-tile.
+// acc[mt][nt][2]: C fragment of DMMA tile (mt, nt) of this warp's (8 TG_MT) x (8 TG_NT) sub-tile.
 // Element (row, col) of the CTA tile held in acc[mt][nt][e]:
-//   row = wm*64 + mt*8 + (lane>>2),  col = wn*32 + nt*8 + (lane&3)*2 + e
-__device__ __forceinline__ void tile_gemm_nt(double (&acc)[8][4][2], const double* __restrict__ A, size_t lda,
+//   row = wm*8*TG_MT + mt*8 + (lane>>2),  col = wn*8*TG_NT + nt*8 + (lane&3)*2 + e
+__device__ __forceinline__ void tile_gemm_nt(double (&acc)[TG_MT][TG_NT][2], const double* __restrict__ A, size_t lda,
                                              const double* __restrict__ B, size_t ldb, int nchunks, double* smem) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wm = warp >> 2, wn = warp & 3;
+  const int wm = warp / TG_WN, wn = warp % TG_WN;
   const int g = lane >> 2, tg = lane & 3;
 
 #pragma unroll
@@ -69,19 +76,19 @@ __device__ __forceinline__ void tile_gemm_nt(double (&acc)[8][4][2], const doubl
       if (nk < nchunks) tg_load_stage(smem + (nk % TG_STAGES) * TG_STAGE_DOUBLES, A, lda, B, ldb, nk * TG_KC);
       cp_async_commit();
     }
-    const double* As = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + (wm * 64 + g) * TG_LDK + tg;
-    const double* Bs = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + NB * TG_LDK + (wn * 32 + g) * TG_LDK + tg;
+    const double* As = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + (wm * 8 * TG_MT + g) * TG_LDK + tg;
+    const double* Bs = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + NB * TG_LDK + (wn * 8 * TG_NT + g) * TG_LDK + tg;
 #pragma unroll
     for (int kk = 0; kk < TG_KC; kk += 4) {
-      double a[8], b[4];
+      double a[TG_MT], b[TG_NT];
 #pragma unroll
-      for (int mt = 0; mt < 8; mt++) a[mt] = As[mt * 8 * TG_LDK + kk];
+      for (int mt = 0; mt < TG_MT; mt++) a[mt] = As[mt * 8 * TG_LDK + kk];
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) b[nt] = Bs[nt * 8 * TG_LDK + kk];
+      for (int nt = 0; nt < TG_NT; nt++) b[nt] = Bs[nt * 8 * TG_LDK + kk];
 #pragma unroll
-      for (int mt = 0; mt < 8; mt++)
+      for (int mt = 0; mt < TG_MT; mt++)
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        for (int nt = 0; nt < TG_NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
     }
   }
   cp_async_wait<0>();

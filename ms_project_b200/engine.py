@@ -51,6 +51,9 @@ class Engine(object):
     def set_profiling(self, on):
         _lib.check(self.ctx, self.lib.b200gp_set_profiling(self.ctx, int(bool(on))), 'b200gp_set_profiling')
 
+    def set_panel_tiles(self, tiles):
+        _lib.check(self.ctx, self.lib.b200gp_set_panel_tiles(self.ctx, int(tiles)), 'b200gp_set_panel_tiles')
+
     def launch_count(self):
         return int(self.lib.b200gp_launch_count(self.ctx))
 

@@ -10,6 +10,8 @@ from ms_project_b200.program import ProgramBatch
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 X, y, k, noise = workloads.config_c5(n=n)
 eng = get_engine(0)
+import os
+if os.environ.get('PANEL'): eng.set_panel_tiles(int(os.environ['PANEL']))
 batch = ProgramBatch([k])
 eng.bind(X, y, 1, batch.max_params)
 eng.upload_programs(batch)

@@ -13,6 +13,8 @@ def main():
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
     X, y, kernels = workloads.config_c2(n=n, n_kernels=m)
     eng = get_engine(0)
+    import os
+    if os.environ.get('PANEL'): eng.set_panel_tiles(int(os.environ['PANEL']))
     batch = ProgramBatch(kernels)
     slots = eng.slots_for(n, 1, m, batch.max_params)
     print('slots', slots, 'max_params', batch.max_params, 'tokens', batch.tokens.shape)
