@@ -111,5 +111,4 @@ class GP(Parameterized):
         self._lml = None
 
     def predict(self, Xnew, full_cov=False, Y_metadata=None, kern=None, likelihood=None, include_likelihood=True):
-        from ..posterior import predict as _predict
-        return _predict(self, Xnew, full_cov=full_cov, include_likelihood=include_likelihood)
+        raise NotImplementedError('posterior prediction is the next row after the scoring path (SURVEY.md 8f, f4)')
