@@ -105,11 +105,13 @@ def cpu_reference_rate(X, y, items, thetas, noises, budget_s, max_items):
     ModelSelector._evaluate_models (src/autoks/core/model_selection/base.py:330)."""
     from oracle import gp as ogp
     from oracle.adapter import to_oracle_expr
-    try:
-        from threadpoolctl import threadpool_info
+    ncpu = len(os.sched_getaffinity(0))
+    try:        # torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host core it can use
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=ncpu)
         cores = max([p.get('num_threads', 1) for p in threadpool_info()] or [1])
     except Exception:
-        cores = len(os.sched_getaffinity(0))
+        cores = ncpu
     done, t0 = 0, time.time()
     for i in range(min(max_items, len(items))):
         try:
@@ -121,6 +123,26 @@ def cpu_reference_rate(X, y, items, thetas, noises, budget_s, max_items):
             break
     dt = time.time() - t0
     return done / dt, cores, done, dt
+
+
+def fit_rate(eng, X, y, items, n_candidates=32):
+    """Secondary figure: FULLY FITTED candidates / s (optimize_restarts with 3 restarts, L-BFGS-B maxfun 1000) for the
+    first `n_candidates` C2 kernels, through the public scoring API (GPModel batch seam), BOMS hyperpriors."""
+    from ms_project_b200 import fitness, workloads
+    from ms_project_b200.covariance import Covariance
+    from ms_project_b200.gp_model import GPModel, score_models
+    from ms_project_b200.gp_models import gp_regression
+    kernels = [items[3 * i].copy() for i in range(n_candidates)]
+    models = [GPModel(Covariance(k)) for k in kernels]
+    md = gp_regression(likelihood_hyperprior={'variance': workloads.boms_hyperpriors()['GP']['variance']})
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    scores = score_models(models, X, y, fitness.negative_bic, n_restarts=N_RESTARTS, engine=eng, model_dict=md)
+    dt = time.perf_counter() - t0
+    evals = sum(m.fit_result.n_evals for m in models)
+    return {'candidates': n_candidates, 'restarts': N_RESTARTS, 'seconds': dt, 'candidates_per_s': n_candidates / dt,
+            'nlml_grad_evaluations': int(evals), 'evaluations_per_s': evals / dt,
+            'failed': int(sum(m.failed_fitting for m in models)), 'best_nbic': float(np.nanmax(scores))}
 
 
 def run_reference(args, rank, world):
@@ -263,6 +285,8 @@ def run_ours(args, rank, world, local_rank):
                           'Kinv': phases[4], 'grad': phases[5], 'items': chunk_items},
             'status_counts': np.bincount(status, minlength=4).tolist(),
         }
+        if world == 1 and not args.no_fit:
+            line['fit'] = fit_rate(eng, X, y, items)
         if world == 1 and not args.no_cpu:
             rate, cores, done, dt = cpu_reference_rate(X, y, items, thetas, noises, budget_s=20.0, max_items=64)
             line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
@@ -279,6 +303,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-fit', action='store_true', help='skip the fitted-candidates/s leg')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
