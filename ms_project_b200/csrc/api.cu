@@ -225,40 +225,65 @@ int b200gp_bind(b200gp_ctx* c, void* ws, size_t ws_bytes, int slots, int max_par
 
 }  // extern "C"
 
-// Right-looking blocked Cholesky of every slot of `b` (M1 in place).
-//  * many slots: plain step loop -- the batch itself fills the GPU;
-//  * few slots (a single large matrix): one-step look-ahead.  The next panel (update of column k+1, its diagonal
-//    factorisation and its TRSM) runs on a high-priority side stream while the main stream is still applying
-//    step k to the rest of the trailing matrix, so the latency-bound panel disappears behind the DMMA update.
-static void cholesky_phase(b200gp_ctx* c, const Batch& b) {
+// Panelled right-looking schedule shared by the Cholesky and the L^-T phases.
+//   panel(k0, k1, stream)      finishes tile columns [k0, k1) given every contribution from the left of k0
+//   update(k0, W, j0, j1, st)  applies panel [k0, k0+W) to the columns [j0, j1) to its right, K = 128 W
+//  * many slots: everything on the context stream -- the batch itself fills the GPU;
+//  * few slots (a single large matrix): look-ahead.  The next panel (its priority update, the latency-bound diagonal
+//    factorisations and the TRSMs) runs on a high-priority side stream while the main stream is still applying the
+//    current panel to the rest of the trailing matrix, so the panel disappears behind the DMMA update.
+template <typename PanelFn, typename UpdateFn>
+static void panel_schedule(b200gp_ctx* c, const Batch& b, PanelFn panel, UpdateFn update) {
   const int T = b.T;
-  const bool la = (b.nslots < 8 && T >= 8);          // look-ahead on the side stream only pays for few, large matrices
+  const bool la = (b.nslots < 8 && T >= 8);
   cudaStream_t s0 = c->stream, s1 = la ? c->side : c->stream;
-  const int W = la ? c->panel_tiles : c->batch_panel_tiles;   // panel width in tiles: trailing updates run with K = 128 W
-  auto panel = [&](int k0, int k1) {                 // factor tile columns [k0, k1) given everything left of k0 applied
-    for (int k = k0; k < k1; k++) {
-      launch_potrf_diag(b, k, s1);
-      if (k + 1 < T) launch_gemm(b, GM_TRSM, k, s1);
-      if (k + 1 < k1) launch_update(b, UpdRange{k, 1, k + 1, k1}, s1);
-    }
-  };
+  const int W = la ? c->panel_tiles : c->batch_panel_tiles;
   if (la) { cudaEventRecord(c->evS, s0); cudaStreamWaitEvent(s1, c->evS, 0); }
-  panel(0, W < T ? W : T);
+  panel(0, W < T ? W : T, s1);
   if (la) cudaEventRecord(c->evP, s1);
   bool have_r = false;
   for (int k0 = 0; k0 + W < T; k0 += W) {
     const int k1 = k0 + W;
-    const int n1 = (k1 + W < T) ? k1 + W : T;        // end of the next panel
-    if (la) cudaStreamWaitEvent(s0, c->evP, 0);              // panel [k0, k1) is factored
-    if (la && have_r) cudaStreamWaitEvent(s1, c->evR, 0);    // columns [k1, n1) have every earlier trailing update
-    launch_update(b, UpdRange{k0, W, k1, n1}, s1);   // look-ahead: the next panel's columns first ...
-    if (n1 < T) launch_update(b, UpdRange{k0, W, n1, T}, s0);   // ... the rest of the trailing matrix meanwhile
+    const int n1 = (k1 + W < T) ? k1 + W : T;                 // end of the next panel
+    if (la) cudaStreamWaitEvent(s0, c->evP, 0);               // panel [k0, k1) is finished
+    if (la && have_r) cudaStreamWaitEvent(s1, c->evR, 0);     // columns [k1, n1) have every earlier trailing update
+    update(k0, W, k1, n1, s1);                                // look-ahead: the next panel's columns first ...
+    if (n1 < T) update(k0, W, n1, T, s0);                     // ... the rest of the trailing matrix meanwhile
     if (la) cudaEventRecord(c->evR, s0);
     have_r = true;
-    panel(k1, n1);
+    panel(k1, n1, s1);
     if (la) cudaEventRecord(c->evP, s1);
   }
   if (la) cudaStreamWaitEvent(s0, c->evP, 0);
+}
+
+// Right-looking blocked Cholesky of every slot of `b` (M1 in place).
+static void cholesky_phase(b200gp_ctx* c, const Batch& b) {
+  const int T = b.T;
+  panel_schedule(
+      c, b,
+      [&](int k0, int k1, cudaStream_t s) {
+        for (int k = k0; k < k1; k++) {
+          launch_potrf_diag(b, k, s);
+          if (k + 1 < T) launch_gemm(b, GM_TRSM, k, s);
+          if (k + 1 < k1) launch_update(b, UpdRange{k, 1, k + 1, k1}, s);
+        }
+      },
+      [&](int k0, int W, int j0, int j1, cudaStream_t s) { launch_update(b, UpdRange{k0, W, j0, j1}, s); });
+}
+
+// Right-looking V = L^-T (upper tiles of M2): column i is finished by V_ji = -S_ji D_i^T (j < i), then pushes its
+// contribution S_jm += V_ji L_mi^T to every column m > i.
+static void inverse_phase(b200gp_ctx* c, const Batch& b) {
+  panel_schedule(
+      c, b,
+      [&](int k0, int k1, cudaStream_t s) {
+        for (int i = k0; i < k1; i++) {
+          if (i > 0) launch_gemm(b, GM_VTRSM, i, s);
+          if (i + 1 < k1) launch_vupdate(b, UpdRange{i, 1, i + 1, k1}, s);
+        }
+      },
+      [&](int k0, int W, int j0, int j1, cudaStream_t s) { launch_vupdate(b, UpdRange{k0, W, j0, j1}, s); });
 }
 
 // Enqueue all phases for one chunk.  Phase events are recorded only when profiling is on.
@@ -271,10 +296,7 @@ static void run_pipeline(b200gp_ctx* c, const Batch& b, int with_grad) {
   if (prof) cudaEventRecord(c->ev[1], s);
   cholesky_phase(c, b);
   if (prof) cudaEventRecord(c->ev[2], s);
-  for (int i = 1; i < b.T; i++) {
-    launch_gemm(b, GM_VACC, i, s);
-    launch_gemm(b, GM_VTRSM, i, s);
-  }
+  inverse_phase(c, b);
   if (prof) cudaEventRecord(c->ev[3], s);
   launch_solve(b, s);
   if (prof) cudaEventRecord(c->ev[4], s);

@@ -149,6 +149,17 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_kernel(Batch b, int mode, 
       alpha = -1.0; beta = -1.0;
       break;
     }
+    case GM_VUPD: {        // S_jm (+)= sum_{i in [max(j,k0), k0+kw)} V_ji L_mi^T
+      const int J = upd.k0 + upd.kw;
+      const int m = upd.j0 + bx / J, j = bx % J;
+      const int kb = j > upd.k0 ? j : upd.k0;
+      C = M2 + (size_t)(j * NB) * ld + m * NB;
+      A = M2 + (size_t)(j * NB) * ld + kb * NB;
+      B = M1 + (size_t)(m * NB) * ld + kb * NB;
+      nchunks = (J - kb) * (NB / TG_KC);
+      beta = (j >= upd.k0) ? 0.0 : 1.0;
+      break;
+    }
     case GM_VACC: {        // S_ji = sum_{k=j}^{i-1} V_jk L_ik^T  (stored where V_ji will live)
       const int i = step, j = bx;
       C = M2 + (size_t)(j * NB) * ld + i * NB;
@@ -224,6 +235,15 @@ void launch_gemm(const Batch& b, int mode, int step, cudaStream_t s) {
   if (ntiles <= 0) return;
   dim3 grid(ntiles, b.nslots);
   gemm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, mode, step, UpdRange{0, 0, 0, 0});
+  g_launch_count++;
+}
+
+void launch_vupdate(const Batch& b, UpdRange r, cudaStream_t s) {
+  const int j1 = r.j1 < b.T ? r.j1 : b.T;
+  const int ntiles = (j1 - r.j0) * (r.k0 + r.kw);
+  if (ntiles <= 0 || r.kw <= 0) return;
+  dim3 grid(ntiles, b.nslots);
+  gemm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, GM_VUPD, r.k0, r);
   g_launch_count++;
 }
 

@@ -40,16 +40,19 @@ struct Batch {
   int add_diag;              // 1: add noise + 1e-8 + jitter to the diagonal (K_y); 0: bare kern.K
 };
 
-enum GemmMode : int { GM_TRSM = 0, GM_SYRK = 1, GM_VACC = 2, GM_VTRSM = 3, GM_KINV = 4, GM_UPD = 5 };
+enum GemmMode : int { GM_TRSM = 0, GM_SYRK = 1, GM_VACC = 2, GM_VTRSM = 3, GM_KINV = 4, GM_UPD = 5, GM_VUPD = 6 };
 
 // GM_UPD: A_ij -= sum_{k in [k0, k0+kw)} L_ik L_jk^T for the tiles with column j in [j0, j1), i >= j.
 struct UpdRange { int k0, kw, j0, j1; };
+// GM_VUPD (right-looking L^-T): S_jm (+)= sum_{i in [max(j,k0), k0+kw)} V_ji L_mi^T for columns m in [j0, j1), rows
+// j < k0+kw; a tile is overwritten when its first contribution arrives (j >= k0), accumulated afterwards.
 
 void launch_build_k(const Batch& b, cudaStream_t s);
 void launch_export_sym(const Batch& b, double* out, cudaStream_t s);       // out[slot][N][N] symmetric copy of M1
 void launch_potrf_diag(const Batch& b, int k, cudaStream_t s);
 void launch_gemm(const Batch& b, int mode, int step, cudaStream_t s);
 void launch_update(const Batch& b, UpdRange r, cudaStream_t s);
+void launch_vupdate(const Batch& b, UpdRange r, cudaStream_t s);
 void launch_solve(const Batch& b, cudaStream_t s);                          // z = L^-1 y, alpha = L^-T z
 void launch_grad(const Batch& b, cudaStream_t s);
 void launch_finalize(const Batch& b, int with_grad, cudaStream_t s);
