@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_kernel(Batch b, int mode, 
   size_t ldb = ld;
   int nchunks;
   double alpha = 1.0, beta = 0.0;
+  bool tri_b = false;      // B is a lower-triangular 128x128 block (D_k): column n only needs k <= n
+  bool tri_a = false;      // the first K tile of A is upper triangular (V_jj): row m only needs k >= m
+  bool diag_c = false;     // C is a diagonal tile: only its lower half is ever read
   const int bx = blockIdx.x;
   switch (mode) {
     case GM_TRSM: {        // L_ik = A_ik D_k^T
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_kernel(Batch b, int mode, 
       B = b.Dinv + ((size_t)slot * b.T + step) * (NB * NB);
       ldb = NB;
       nchunks = NB / TG_KC;
+      tri_b = true;
       break;
     }
     case GM_SYRK: {        // A_ij -= L_ik L_jk^T
@@ -147,6 +151,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_kernel(Batch b, int mode, 
       B = M1 + (size_t)(j * NB) * ld + upd.k0 * NB;
       nchunks = upd.kw * (NB / TG_KC);
       alpha = -1.0; beta = -1.0;
+      diag_c = (i == j);
       break;
     }
     case GM_VUPD: {        // S_jm (+)= sum_{i in [max(j,k0), k0+kw)} V_ji L_mi^T
@@ -158,6 +163,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_kernel(Batch b, int mode, 
       B = M1 + (size_t)(m * NB) * ld + kb * NB;
       nchunks = (J - kb) * (NB / TG_KC);
       beta = (j >= upd.k0) ? 0.0 : 1.0;
+      tri_a = (kb == j);
       break;
     }
     case GM_VACC: {        // S_ji = sum_{k=j}^{i-1} V_jk L_ik^T  (stored where V_ji will live)
@@ -176,6 +182,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_kernel(Batch b, int mode, 
       ldb = NB;
       nchunks = NB / TG_KC;
       alpha = -1.0;
+      tri_b = true;
       break;
     }
     default: {             // GM_KINV: (K^-1)_ij = sum_{k>=i} V_ik V_jk^T
@@ -185,12 +192,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_kernel(Batch b, int mode, 
       A = M2 + (size_t)(i * NB) * ld + i * NB;
       B = M2 + (size_t)(j * NB) * ld + i * NB;
       nchunks = (b.T - i) * (NB / TG_KC);
+      tri_a = true;
+      diag_c = (i == j);
       break;
     }
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wm = warp / TG_WN, wn = warp % TG_WN, g = lane >> 2, tg = lane & 3;
+  const int g = lane >> 2, tg = lane & 3;
+  int wm, wn;
+  warp_coords(warp, wm, wn);
   double* Cw = C + (size_t)(wm * 8 * TG_MT + g) * ld + wn * 8 * TG_NT + tg * 2;
 
   double acc[TG_MT][TG_NT][2];
@@ -210,7 +221,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) gemm_kernel(Batch b, int mode, 
       for (int nt = 0; nt < TG_NT; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
   }
 
-  tile_gemm_nt(acc, A, ld, B, ldb, nchunks, smem);
+  // structural zeros, resolved per warp (rows [wm*8*TG_MT, +8*TG_MT), columns [wn*8*TG_NT, +8*TG_NT))
+  int kc_lo = 0, kc_hi = nchunks;
+  if (tri_b) kc_hi = ((wn + 1) * 8 * TG_NT + TG_KC - 1) / TG_KC;
+  if (tri_a) kc_lo = (wm * 8 * TG_MT) / TG_KC;
+  if (diag_c && wn * TG_NT > wm * TG_MT + TG_MT - 1) kc_hi = 0;     // warp tile strictly above the diagonal
+  tile_gemm_nt(acc, A, ld, B, ldb, nchunks, smem, kc_lo, kc_hi);
 
 #pragma unroll
   for (int mt = 0; mt < TG_MT; mt++)

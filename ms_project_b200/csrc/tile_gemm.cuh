@@ -8,6 +8,8 @@
 //   * operands stream global -> shared through a 4-stage cp.async (LDGSTS) ring, 16 doubles of K
 //     per stage, rows padded to 20 doubles so the 64-bit fragment loads are bank-conflict free
 //   * one __syncthreads per stage
+//   * [kc_lo, kc_hi): per-warp range of K-chunks that can contribute (triangular operands / diagonal output tiles);
+//     outside it the warp still takes part in the copies and barriers but issues no DMMA
 #pragma once
 #include "common.cuh"
 
@@ -35,6 +37,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// Warp -> (wm, wn) position in the TG_WM x TG_WN warp grid.  A warp lives on SM sub-partition (warp % 4); the columns
+// are rotated against the rows so every sub-partition hosts one warp of EACH wn and of each wm.  The structural-zero
+// skips below (which depend on wn, on wm, or on wn > wm) then shorten all four DMMA pipes evenly.
+__device__ __forceinline__ void warp_coords(int warp, int& wm, int& wn) {
+  wm = warp / TG_WN;
+  wn = (warp - wm) & (TG_WN - 1);
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -58,9 +68,11 @@ __device__ __forceinline__ void tg_load_stage(double* stage, const double* __res
 // Element (row, col) of the CTA tile held in acc[mt][nt][e]:
 //   row = wm*8*TG_MT + mt*8 + (lane>>2),  col = wn*8*TG_NT + nt*8 + (lane&3)*2 + e
 __device__ __forceinline__ void tile_gemm_nt(double (&acc)[TG_MT][TG_NT][2], const double* __restrict__ A, size_t lda,
-                                             const double* __restrict__ B, size_t ldb, int nchunks, double* smem) {
+                                             const double* __restrict__ B, size_t ldb, int nchunks, double* smem,
+                                             int kc_lo = 0, int kc_hi = 1 << 30) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wm = warp / TG_WN, wn = warp % TG_WN;
+  int wm, wn;
+  warp_coords(warp, wm, wn);
   const int g = lane >> 2, tg = lane & 3;
 
 #pragma unroll
@@ -78,6 +90,7 @@ __device__ __forceinline__ void tile_gemm_nt(double (&acc)[TG_MT][TG_NT][2], con
     }
     const double* As = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + (wm * 8 * TG_MT + g) * TG_LDK + tg;
     const double* Bs = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + NB * TG_LDK + (wn * 8 * TG_NT + g) * TG_LDK + tg;
+    if (kc < kc_lo || kc >= kc_hi) continue;     // warp-uniform: this warp's operands are structurally zero here
 #pragma unroll
     for (int kk = 0; kk < TG_KC; kk += 4) {
       double a[TG_MT], b[TG_NT];
