@@ -278,7 +278,7 @@ def run_ours(args, rank, world, local_rank):
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                         'traffic': None, 'kernel': 'gemm_kernel (FP64 DMMA tile GEMM: Cholesky + L^-T + K^-1 phases)',
+                         'traffic': None, 'kernel': 'chol_update_kernel + inv_update_kernel + kinv_kernel + *_trsm_kernel (FP64 DMMA tile GEMM: Cholesky + L^-T + K^-1 phases)',
                          'algorithmic': 'N^3 flops per item (N^3/3 Cholesky + N^3/3 triangular inverse + N^3/3 K^-1)',
                          'peak_source': peak_src},
             'phases_ms': {'build_K': phases[0], 'cholesky': phases[1], 'inverse': phases[2], 'solve': phases[3],

@@ -40,7 +40,7 @@ struct Batch {
   int add_diag;              // 1: add noise + 1e-8 + jitter to the diagonal (K_y); 0: bare kern.K
 };
 
-enum GemmMode : int { GM_TRSM = 0, GM_SYRK = 1, GM_VACC = 2, GM_VTRSM = 3, GM_KINV = 4, GM_UPD = 5, GM_VUPD = 6 };
+enum GemmMode : int { GM_TRSM = 0, GM_VTRSM = 3, GM_KINV = 4, GM_UPD = 5, GM_VUPD = 6 };
 
 // GM_UPD: A_ij -= sum_{k in [k0, k0+kw)} L_ik L_jk^T for the tiles with column j in [j0, j1), i >= j.
 struct UpdRange { int k0, kw, j0, j1; };

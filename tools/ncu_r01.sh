@@ -1,10 +1,26 @@
-set -e
-CMD="python tools/perf_probe.py 2048 32 1"
-$CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r01.csv $CMD > gpurun_out/ncu0.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 60 -c 1 -f -o gpurun_out/prof_kinv $CMD > gpurun_out/ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 1 -c 1 -f -o gpurun_out/prof_syrk $CMD > gpurun_out/ncu2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:grad_kernel -c 1 -f -o gpurun_out/prof_grad $CMD > gpurun_out/ncu3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:build_k_kernel -c 1 -f -o gpurun_out/prof_build $CMD > gpurun_out/ncu4.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:potrf_diag -s 3 -c 1 -f -o gpurun_out/prof_potrf $CMD > gpurun_out/ncu5.log 2>&1
-tail -3 gpurun_out/plain.log; ls -la gpurun_out
+#!/bin/bash
+# One gpurun call: GPU tests, bench line, ncu launch list of the SAME bench command, one --set full capture per kernel.
+# Usage (from the repo root on the GPU box):  bash tools/ncu_r01.sh <tag>
+TAG=${1:-r01}
+O=gpurun_out
+mkdir -p $O
+python -m pytest tests -m gpu -x -q > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu_$TAG.log
+tail -3 $O/pytest_gpu_$TAG.log
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu --no-fit"
+$BENCH > $O/bench_plain_$TAG.json 2> $O/bench_plain_$TAG.err && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_$TAG.csv $BENCH > $O/ncu_launch_$TAG.log 2>&1
+PROBE="python tools/perf_probe.py 2048 32 1"
+$PROBE > $O/probe_plain_$TAG.log 2>&1 || exit 1
+cap() {  # name, kernel regex, skip
+  ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o $O/prof_$1_$TAG $PROBE > $O/ncu_$1_$TAG.log 2>&1
+}
+cap upd chol_update_kernel 1
+cap vupd inv_update_kernel 3
+cap kinv kinv_kernel 0
+cap trsm chol_trsm_kernel 2
+cap grad grad_kernel 0
+cap build build_k_kernel 0
+cap potrf potrf_diag 3
+python bench.py --steps 5 --warmup 3 > $O/bench_$TAG.json 2> $O/bench_$TAG.err
+tail -c 600 $O/bench_$TAG.json
+ls -la $O | tail -20
