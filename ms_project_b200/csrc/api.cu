@@ -79,7 +79,8 @@ struct Carver {
 
 struct Layout {
   double *M1, *M2, *Dinv, *z, *alpha, *logdet_part, *diag_part, *grad_part, *Xt, *y, *jitter;
-  int *slot_status, *ids;
+  int *slot_status, *ids, *klist, *kcount;
+  CProg* cprog;
   size_t bytes;
 };
 
@@ -101,6 +102,9 @@ Layout carve(void* ws, int N, int D, int slots, int max_params) {
   l.jitter = c.take<double>(S);
   l.slot_status = c.take<int>(S);
   l.ids = c.take<int>(S);
+  l.cprog = c.take<CProg>(S);
+  l.klist = c.take<int>(S * CK_KINDS);
+  l.kcount = c.take<int>(CK_KINDS);
   l.bytes = c.off + 256;
   return l;
 }
@@ -204,6 +208,7 @@ int b200gp_bind(b200gp_ctx* c, void* ws, size_t ws_bytes, int slots, int max_par
   b.pstride = max_params + 1;
   b.slot_status = l.slot_status;
   b.Xt = l.Xt; b.y = l.y;
+  b.cprog = l.cprog; b.klist = l.klist; b.kcount = l.kcount; b.list_stride = slots;
   c->ws_jitter = l.jitter; c->ws_ids = l.ids;
   c->slots = slots; c->max_params = max_params;
   launch_pack_data(dX, dy, N, D, b.Np, l.Xt, l.y, c->stream);
@@ -292,6 +297,7 @@ static void run_pipeline(b200gp_ctx* c, const Batch& b, int with_grad) {
   const bool prof = c->profiling;
   cudaMemsetAsync(b.slot_status, 0, sizeof(int) * b.nslots, s);
   if (prof) cudaEventRecord(c->ev[0], s);
+  launch_compile(b, s);
   launch_build_k(b, s);
   if (prof) cudaEventRecord(c->ev[1], s);
   cholesky_phase(c, b);
@@ -330,6 +336,7 @@ int b200gp_build_K(b200gp_ctx* c, const int32_t* prog, const int32_t* prog_off, 
     b.prog = reinterpret_cast<const int4*>(prog); b.prog_off = prog_off; b.theta = theta; b.theta_off = theta_off;
     b.quirks = c->quirks;
     b.add_diag = add_diag;
+    launch_compile(b, c->stream);
     launch_build_k(b, c->stream);
     launch_export_sym(b, K_out + (size_t)off * n2, c->stream);
   }

@@ -5,13 +5,462 @@
 // The gradient pass replaces `kern.update_gradients_full(dL_dK, X)` and the Gaussian likelihood's
 // `exact_inference_gradients`: dL/dtheta_p = sum_ij 1/2 (alpha_i alpha_j - K^-1_ij) dK_ij/dtheta_p with
 // dK regenerated from X in registers, so neither dL/dK nor dK ever exists in HBM.
+//
+// Two implementations share the work of one chunk (the compile kernel sorts the slots into lists):
+//   * poly kernels  -- programs with <= 8 leaves run in the register-resident polynomial form of cprog.cuh;
+//   * interp kernels -- everything else runs the generic postfix interpreter of kprog.cuh.
+// All of them are persistent (grid = resident CTAs, grid-stride over (slot, tile) work items), so an empty list
+// costs one wave of CTAs that exit at once.
 #include "kernels.cuh"
 #include "kprog.cuh"
+#include "cprog.cuh"
 
 namespace b200gp {
 
 constexpr double EXACT_INFERENCE_JITTER = 1e-8;   // GPy exact_gaussian_inference.py: diag.add(Ky, variance + 1e-8)
 
+
+static int g_sm_count = 148;
+static int g_grid_poly_build[2] = {296, 148}, g_grid_poly_grad[2] = {296, 148}, g_grid_interp_build = 592, g_grid_interp_grad = 592;
+
+// ------------------------------------------------------------------------------------------------
+// Compile: postfix program -> CProg per slot, then the per-kind slot lists (slot order preserved).
+// ------------------------------------------------------------------------------------------------
+__device__ void compile_one(const Batch& b, int slot) {
+  const int item = b.ids[slot];
+  const int t0 = b.prog_off[item], nt = b.prog_off[item + 1] - t0;
+  CProg& cp = b.cprog[slot];
+  cp.nparam = b.theta_off[item + 1] - b.theta_off[item] - 1;
+  cp.pad = 0;
+  int L = 0, G = 0, single = 0, kind = CK_GENERIC;
+  if (nt <= CP_MAXTOK) {
+    unsigned char masks[CP_MAXTOK][CP_GMAX];
+    unsigned char cnt[CP_MAXTOK];
+    bool ok = true;
+    for (int t = 0; t < nt && ok; t++) {
+      const int4 k = b.prog[t0 + t];
+      if (k.x <= OP_CONST) {
+        if (L >= CP_LMAX) { ok = false; break; }
+        cp.leaf[L] = make_int4(k.x, k.y, k.z, leaf_param_count(k.x));
+        masks[t][0] = (unsigned char)(1u << L);
+        cnt[t] = 1;
+        L++;
+      } else if (k.x == OP_ADD) {
+        const int na = cnt[k.y], nb = cnt[k.z];
+        if (na + nb > CP_GMAX) { ok = false; break; }
+        for (int i = 0; i < na; i++) masks[t][i] = masks[k.y][i];
+        for (int i = 0; i < nb; i++) masks[t][na + i] = masks[k.z][i];
+        cnt[t] = (unsigned char)(na + nb);
+      } else {
+        const int na = cnt[k.y], nb = cnt[k.z];
+        if (na * nb > CP_GMAX) { ok = false; break; }
+        for (int i = 0; i < na; i++)
+          for (int j = 0; j < nb; j++) masks[t][i * nb + j] = masks[k.y][i] | masks[k.z][j];
+        cnt[t] = (unsigned char)(na * nb);
+      }
+    }
+    if (ok && nt > 0) {
+      G = cnt[nt - 1];
+      single = 1;
+      for (int i = 0; i < G; i++) {
+        cp.term[i] = masks[nt - 1][i];
+        if (__popc((unsigned)masks[nt - 1][i]) != 1) single = 0;
+      }
+      kind = (L <= 4) ? CK_POLY4 : CK_POLY8;
+    }
+  }
+  for (int i = L; i < CP_LMAX; i++) cp.leaf[i] = make_int4(OP_CONST, 0, 0, 0);
+  for (int i = G; i < 24; i++) cp.term[i] = 0;
+  cp.kind = kind; cp.L = L; cp.G = G; cp.single = single;
+}
+
+__global__ void __launch_bounds__(256) compile_programs_kernel(Batch b) {
+  for (int slot = threadIdx.x; slot < b.nslots; slot += blockDim.x) compile_one(b, slot);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int cnt[CK_KINDS] = {0, 0, 0};
+    for (int base = 0; base < b.nslots; base += 32) {
+      const int slot = base + lane;
+      const int kind = slot < b.nslots ? b.cprog[slot].kind : -1;
+#pragma unroll
+      for (int k = 0; k < CK_KINDS; k++) {
+        const unsigned m = __ballot_sync(0xffffffffu, kind == k);
+        if (kind == k) b.klist[k * b.list_stride + cnt[k] + __popc(m & ((1u << lane) - 1u))] = slot;
+        cnt[k] += __popc(m);
+      }
+    }
+    if (lane < CK_KINDS) b.kcount[lane] = cnt[lane];
+  }
+}
+
+void launch_compile(const Batch& b, cudaStream_t s) {
+  compile_programs_kernel<<<1, 256, 0, s>>>(b);
+  g_launch_count++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Polynomial-form kernels.  Thread (c, h) of a 256-thread CTA owns column c = tid & 127 of the 128 x 128 tile and
+// the rows [64 h, 64 h + 64): its column-side point values stay in registers for the whole tile, the row-side
+// values are broadcast reads of shared memory, global accesses are 256-byte row segments per warp.
+// ------------------------------------------------------------------------------------------------
+template <int LMAX>
+struct PolySmem {
+  CProg cp;
+  double cst[LMAX][4];          // per leaf: SE {v, 1/l}; RQ {v, 1/l, a, 1/2a}; PER {v, pi/p, 1/l, 1/p}; LIN {v, shift}
+  double ivar[LMAX];
+  double Ai[LMAX][NB];          // row-side point value: x (SE, RQ), pi x / p (PER), x - shift (LIN)
+  double Si[LMAX][NB];          // PER: sin / cos of Ai, so sin(a_i - a_j) needs no per-pair sincos
+  double Ci[LMAX][NB];
+  double ai[NB];                // alpha_i (gradient pass) / diagonal staging (build)
+  double red[8][3 * LMAX + 1];
+  double noise;
+};
+
+__device__ __forceinline__ void leaf_constants(int op, const double* __restrict__ th, double* cst, double& ivar) {
+  double c0 = th[0], c1 = 0, c2 = 0, c3 = 0;
+  switch (op) {
+    case OP_SE:  c1 = 1.0 / th[1]; break;
+    case OP_RQ:  c1 = 1.0 / th[1]; c2 = th[2]; c3 = 1.0 / (2.0 * th[2]); break;
+    case OP_PER: c1 = 3.14159265358979323846 / th[1]; c2 = 1.0 / th[2]; c3 = 1.0 / th[1]; break;
+    case OP_LIN: c1 = th[1]; break;
+    default: break;
+  }
+  cst[0] = c0; cst[1] = c1; cst[2] = c2; cst[3] = c3;
+  ivar = 1.0 / c0;
+}
+
+__device__ __forceinline__ void point_values(int op, const double* cst, double x, double& A, double& S, double& C) {
+  S = 0.0; C = 0.0;
+  if (op == OP_PER) { A = x * cst[1]; sincos(A, &S, &C); }
+  else if (op == OP_LIN) A = x - cst[1];
+  else A = x;
+}
+
+// Leaf values for E rows of one column.  aux keeps what the reverse sweep cannot cheaply recompute.
+template <int E>
+__device__ __forceinline__ void leaf_fwd(int op, const double* cst, const double* Ar, const double* Sr, const double* Cr,
+                                         double Aj, double Sj, double Cj, double (&v)[E], double (&aux)[E]) {
+  const double c0 = cst[0];
+  switch (op) {
+    case OP_SE: {        // rbf.ipynb#1-2: v exp(-r^2 / 2)
+      const double c1 = cst[1];
+#pragma unroll
+      for (int e = 0; e < E; e++) { const double r = (Ar[e] - Aj) * c1; const double a = r * r; aux[e] = a; v[e] = c0 * exp(-0.5 * a); }
+      break;
+    }
+    case OP_RQ: {        // rational-quadratic.ipynb#2: v exp(-a log1p(r^2 / 2a))
+      const double c1 = cst[1], c2 = cst[2], c3 = cst[3];
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const double r = (Ar[e] - Aj) * c1;
+        const double lg = log1p((r * r) * c3);
+        aux[e] = lg;
+        v[e] = c0 * exp(-c2 * lg);
+      }
+      break;
+    }
+    case OP_PER: {       // periodic.ipynb#2: v exp(-2 sin^2(pi (x - x') / p) / l^2), sin(a_i - a_j) by the angle-difference identity
+      const double il = cst[2];
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const double s = Sr[e] * Cj - Cr[e] * Sj;
+        const double q = s * il;
+        aux[e] = s;
+        v[e] = c0 * exp(-2.0 * (q * q));
+      }
+      break;
+    }
+    case OP_LIN: {       // linear.ipynb#2: v (x - c)(x' - c)
+#pragma unroll
+      for (int e = 0; e < E; e++) { aux[e] = Ar[e] * Aj; v[e] = c0 * aux[e]; }
+      break;
+    }
+    default: {
+#pragma unroll
+      for (int e = 0; e < E; e++) { aux[e] = 0.0; v[e] = c0; }
+      break;
+    }
+  }
+}
+
+// acc[p] += sum_e g[e] dv/dtheta_p for the leaf's own parameters (same formulas as kprog.cuh eval_grad).
+template <int E>
+__device__ __forceinline__ void leaf_bwd(int op, const double* cst, double ivar, const double* Ar, const double* Sr,
+                                         const double* Cr, double Aj, double Sj, double Cj, const double (&g)[E],
+                                         const double (&v)[E], const double (&aux)[E], double (&acc)[3], int quirks) {
+  switch (op) {
+    case OP_SE: {
+      const double c1 = cst[1];
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const double gv = g[e] * v[e];
+        acc[0] = fma(gv, ivar, acc[0]);
+        acc[1] = fma(gv, aux[e] * c1, acc[1]);
+      }
+      break;
+    }
+    case OP_RQ: {
+      const double c1 = cst[1], c2 = cst[2], c3 = cst[3];
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const double r = (Ar[e] - Aj) * c1;
+        const double u = (r * r) * c3;
+        const double e1 = 1.0 / (1.0 + u);
+        const double gv = g[e] * v[e];
+        acc[0] = fma(gv, ivar, acc[0]);
+        acc[1] = fma(gv, (u * (2.0 * c2)) * c1 * e1, acc[1]);
+        acc[2] = fma(gv, u * e1 - aux[e], acc[2]);
+      }
+      break;
+    }
+    case OP_PER: {
+      const double il = cst[2], ip = cst[3];
+      const double lsf = (quirks & QUIRK_PER_LENGTHSCALE) ? 1.0 : 4.0;
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const double s = aux[e];
+        const double c = Cr[e] * Cj + Sr[e] * Sj;
+        const double base = Ar[e] - Aj;
+        const double q = s * il;
+        const double gv = g[e] * v[e];
+        acc[0] = fma(gv, ivar, acc[0]);
+        acc[1] = fma(gv, (4.0 * il * il) * s * c * (base * ip), acc[1]);
+        acc[2] = fma(gv, lsf * (q * q) * il, acc[2]);
+      }
+      break;
+    }
+    case OP_LIN: {
+      const double sf = (quirks & QUIRK_LIN_SHIFT) ? 1.0 : cst[0];
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        acc[0] = fma(g[e], aux[e], acc[0]);
+        acc[1] = fma(g[e], sf * (-(Ar[e] + Aj)), acc[1]);
+      }
+      break;
+    }
+    default: {
+#pragma unroll
+      for (int e = 0; e < E; e++) acc[0] += g[e];
+      break;
+    }
+  }
+}
+
+// Cooperative prologue of one (slot, tile) work item: program, leaf constants, row-side tables; returns the
+// column-side values of this thread's column in registers.
+template <int LMAX>
+__device__ __forceinline__ void poly_prologue(PolySmem<LMAX>& S, const Batch& b, int slot, int ti, int tj,
+                                              double (&Aj)[LMAX], double (&Sj)[LMAX], double (&Cj)[LMAX]) {
+  __syncthreads();                                           // the previous work item is done with S
+  if (threadIdx.x < (int)(sizeof(CProg) / 4))
+    reinterpret_cast<int*>(&S.cp)[threadIdx.x] = reinterpret_cast<const int*>(&b.cprog[slot])[threadIdx.x];
+  __syncthreads();
+  const int item = b.ids[slot];
+  const int th0 = b.theta_off[item];
+  const int L = S.cp.L;
+  if (threadIdx.x < L) leaf_constants(S.cp.leaf[threadIdx.x].x, b.theta + th0 + S.cp.leaf[threadIdx.x].z, S.cst[threadIdx.x], S.ivar[threadIdx.x]);
+  if (threadIdx.x == 32) S.noise = b.theta[b.theta_off[item + 1] - 1];
+  __syncthreads();
+  const int c = threadIdx.x & (NB - 1);
+  if (threadIdx.x < NB) {
+#pragma unroll
+    for (int l = 0; l < LMAX; l++)
+      if (l < L) {
+        const int4 lf = S.cp.leaf[l];
+        double A, Sv, Cv;
+        point_values(lf.x, S.cst[l], b.Xt[(size_t)lf.y * b.Np + ti * NB + c], A, Sv, Cv);
+        S.Ai[l][c] = A; S.Si[l][c] = Sv; S.Ci[l][c] = Cv;
+      }
+  }
+#pragma unroll
+  for (int l = 0; l < LMAX; l++) {
+    Aj[l] = 0.0; Sj[l] = 0.0; Cj[l] = 0.0;
+    if (l < L) {
+      const int4 lf = S.cp.leaf[l];
+      point_values(lf.x, S.cst[l], b.Xt[(size_t)lf.y * b.Np + tj * NB + c], Aj[l], Sj[l], Cj[l]);
+    }
+  }
+}
+
+template <int LMAX, int E>
+__global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_build_kernel(Batch b, int kind) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PolySmem<LMAX>& S = *reinterpret_cast<PolySmem<LMAX>*>(smem_raw);
+  const int count = b.kcount[kind];
+  const int* list = b.klist + kind * b.list_stride;
+  const int ntiles = tri_count(b.T);
+  const long long nwork = (long long)count * ntiles;
+  const int c = threadIdx.x & (NB - 1), h = threadIdx.x >> 7;
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int slot = list[w / ntiles];
+    int ti, tj;
+    tri_decode((int)(w % ntiles), ti, tj);
+    double Aj[LMAX], Sj[LMAX], Cj[LMAX];
+    poly_prologue<LMAX>(S, b, slot, ti, tj, Aj, Sj, Cj);
+    __syncthreads();
+    const int L = S.cp.L, G = S.cp.G;
+    const double diag_add = b.add_diag ? S.noise + EXACT_INFERENCE_JITTER + (b.jitter ? b.jitter[slot] : 0.0) : 0.0;
+    double* out = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB + c;
+    const int gj = tj * NB + c;
+#pragma unroll 1
+    for (int r0 = h * 64; r0 < h * 64 + 64; r0 += E) {
+      double v[LMAX][E], aux[E];
+#pragma unroll
+      for (int l = 0; l < LMAX; l++)
+        if (l < L) leaf_fwd<E>(S.cp.leaf[l].x, S.cst[l], &S.Ai[l][r0], &S.Si[l][r0], &S.Ci[l][r0], Aj[l], Sj[l], Cj[l], v[l], aux);
+      double k[E];
+#pragma unroll
+      for (int e = 0; e < E; e++) k[e] = 0.0;
+      for (int g = 0; g < G; g++) {
+        const unsigned mask = S.cp.term[g];
+        double p[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) p[e] = 1.0;
+#pragma unroll
+        for (int l = 0; l < LMAX; l++)
+          if (mask & (1u << l)) {
+#pragma unroll
+            for (int e = 0; e < E; e++) p[e] *= v[l][e];
+          }
+#pragma unroll
+        for (int e = 0; e < E; e++) k[e] += p[e];
+      }
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const int gi = ti * NB + r0 + e;
+        double val = k[e];
+        if (gi >= b.N || gj >= b.N) val = (gi == gj) ? 1.0 : 0.0;
+        else if (gi == gj) { val += diag_add; S.ai[c] = val; }
+        out[(size_t)(r0 + e) * b.Np] = val;
+      }
+    }
+    if (ti == tj) {    // deterministic partial of trace(K_y) for the jitter ladder
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int t = 0; t < NB; t++)
+          if (ti * NB + t < b.N) s += S.ai[t];
+        b.diag_part[slot * b.T + ti] = s;
+      }
+    }
+  }
+}
+
+template <int LMAX, int E>
+__global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_grad_kernel(Batch b, int kind) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PolySmem<LMAX>& S = *reinterpret_cast<PolySmem<LMAX>*>(smem_raw);
+  constexpr int NV = 3 * LMAX + 1;
+  const int count = b.kcount[kind];
+  const int* list = b.klist + kind * b.list_stride;
+  const int ntiles = tri_count(b.T);
+  const long long nwork = (long long)count * ntiles;
+  const int c = threadIdx.x & (NB - 1), h = threadIdx.x >> 7;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int slot = list[w / ntiles];
+    if (b.slot_status[slot] != 0) continue;
+    const int tile = (int)(w % ntiles);
+    int ti, tj;
+    tri_decode(tile, ti, tj);
+    double Aj[LMAX], Sj[LMAX], Cj[LMAX];
+    poly_prologue<LMAX>(S, b, slot, ti, tj, Aj, Sj, Cj);
+    if (threadIdx.x >= NB) S.ai[c] = b.alpha[(size_t)slot * b.Np + ti * NB + c];
+    const double aj = b.alpha[(size_t)slot * b.Np + tj * NB + c];
+    __syncthreads();
+    const int L = S.cp.L, G = S.cp.G, single = S.cp.single;
+    double acc[LMAX][3], accn = 0.0;
+#pragma unroll
+    for (int l = 0; l < LMAX; l++) { acc[l][0] = 0.0; acc[l][1] = 0.0; acc[l][2] = 0.0; }
+    const double* Kinv = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB + c;
+    const int gj = tj * NB + c;
+    // diagonal tiles: rows above this warp's first column hold no lower-triangle element
+    int rbeg = h * 64;
+    if (ti == tj) { const int cmin = c - lane; if (cmin > rbeg) rbeg = cmin / E * E; }
+    const int rend = h * 64 + 64;
+    double kv[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) kv[e] = (rbeg < rend) ? Kinv[(size_t)(rbeg + e) * b.Np] : 0.0;
+#pragma unroll 1
+    for (int r0 = rbeg; r0 < rend; r0 += E) {
+      double wt[E];
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const int gi = ti * NB + r0 + e;
+        double wv = 0.5 * (S.ai[r0 + e] * aj - kv[e]);
+        const bool valid = gi < b.N && gj <= gi;       // gj <= gi < N
+        if (gi == gj) { if (valid) accn += wv; } else wv *= 2.0;      // symmetric pair (i, j), (j, i)
+        wt[e] = valid ? wv : 0.0;
+      }
+      if (r0 + E < rend) {
+#pragma unroll
+        for (int e = 0; e < E; e++) kv[e] = Kinv[(size_t)(r0 + E + e) * b.Np];
+      }
+      double v[LMAX][E], aux[LMAX][E];
+#pragma unroll
+      for (int l = 0; l < LMAX; l++)
+        if (l < L) leaf_fwd<E>(S.cp.leaf[l].x, S.cst[l], &S.Ai[l][r0], &S.Si[l][r0], &S.Ci[l][r0], Aj[l], Sj[l], Cj[l], v[l], aux[l]);
+#pragma unroll
+      for (int l = 0; l < LMAX; l++)
+        if (l < L) {
+          double g[E];
+          if (single) {
+#pragma unroll
+            for (int e = 0; e < E; e++) g[e] = wt[e];
+          } else {
+            double adj[E];
+#pragma unroll
+            for (int e = 0; e < E; e++) adj[e] = 0.0;
+            for (int t = 0; t < G; t++) {
+              const unsigned mask = S.cp.term[t];
+              if (!(mask & (1u << l))) continue;
+              double p[E];
+#pragma unroll
+              for (int e = 0; e < E; e++) p[e] = 1.0;
+#pragma unroll
+              for (int m = 0; m < LMAX; m++)
+                if (m != l && (mask & (1u << m))) {
+#pragma unroll
+                  for (int e = 0; e < E; e++) p[e] *= v[m][e];
+                }
+#pragma unroll
+              for (int e = 0; e < E; e++) adj[e] += p[e];
+            }
+#pragma unroll
+            for (int e = 0; e < E; e++) g[e] = wt[e] * adj[e];
+          }
+          leaf_bwd<E>(S.cp.leaf[l].x, S.cst[l], S.ivar[l], &S.Ai[l][r0], &S.Si[l][r0], &S.Ci[l][r0], Aj[l], Sj[l], Cj[l], g,
+                      v[l], aux[l], acc[l], b.quirks);
+        }
+    }
+    // CTA reduction in a fixed order: lanes (shuffle tree), then the 8 warps
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      double x = (i == NV - 1) ? accn : acc[i / 3][i % 3];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane == 0) S.red[warp][i] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+      const int i = threadIdx.x;
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) s += S.red[q][i];
+      double* out = b.grad_part + ((size_t)slot * ntiles + tile) * b.pstride;
+      if (i == NV - 1) out[S.cp.nparam] = s;
+      else {
+        const int l = i / 3, p = i % 3;
+        if (l < L && p < S.cp.leaf[l].w) out[S.cp.leaf[l].z + p] = s;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Interpreter kernels (programs the polynomial form cannot hold): one 128 x 128 tile per work item.
+// ------------------------------------------------------------------------------------------------
 struct ElemSmem {
   ProgSmem P;
   double xi[MAX_DIMS * NB];
@@ -28,53 +477,129 @@ __device__ __forceinline__ void stage_inputs(ElemSmem& S, const Batch& b, int ti
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K-build: one CTA per lower tile (ti >= tj) per slot; writes the full 128x128 tile of
-// K + (noise + 1e-8 + jitter) I, identity in the padding.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) build_k_kernel(Batch b) {
+__global__ void __launch_bounds__(256) interp_build_kernel(Batch b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ElemSmem& S = *reinterpret_cast<ElemSmem*>(smem_raw);
-  const int slot = blockIdx.y, item = b.ids[slot];
-  int ti, tj;
-  tri_decode(blockIdx.x, ti, tj);
-  load_program(S.P, b.prog, b.prog_off, b.theta, b.theta_off, item);
-  stage_inputs(S, b, ti, tj);
-  __syncthreads();
-  const double diag_add = b.add_diag ? S.P.noise + EXACT_INFERENCE_JITTER + (b.jitter ? b.jitter[slot] : 0.0) : 0.0;
+  const int count = b.kcount[CK_GENERIC];
+  const int* list = b.klist + CK_GENERIC * b.list_stride;
+  const int ntiles = tri_count(b.T);
+  const long long nwork = (long long)count * ntiles;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* out = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB;
-  double dsum = 0.0;
-  // thread -> 64 elements: rows warp + 8k (k < 16), columns lane + 32m (m < 4): every warp store is one
-  // 256-byte row segment.  One copy of the interpreter in the instruction stream (no unrolling).
-#pragma unroll 1
-  for (int it = 0; it < 64; it++) {
-    const int r = warp + 8 * (it >> 2), c = lane + 32 * (it & 3);
-    const int gi = ti * NB + r, gj = tj * NB + c;
-    double v;
-    if (gi >= b.N || gj >= b.N) {
-      v = (gi == gj) ? 1.0 : 0.0;
-    } else {
-      v = eval_K(S.P, S.xi + r, S.xj + c, NB);
-      if (gi == gj) { v += diag_add; dsum += v; }
-    }
-    out[(size_t)r * b.Np + c] = v;
-  }
-  if (ti == tj) {   // deterministic partial of trace(K_y) for the jitter ladder
-    S.red[threadIdx.x] = dsum;
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int slot = list[w / ntiles], item = b.ids[slot];
+    int ti, tj;
+    tri_decode((int)(w % ntiles), ti, tj);
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double s = 0.0;
-      for (int t = 0; t < 256; t++) s += S.red[t];
-      b.diag_part[slot * b.T + ti] = s;
+    load_program(S.P, b.prog, b.prog_off, b.theta, b.theta_off, item);
+    stage_inputs(S, b, ti, tj);
+    __syncthreads();
+    const double diag_add = b.add_diag ? S.P.noise + EXACT_INFERENCE_JITTER + (b.jitter ? b.jitter[slot] : 0.0) : 0.0;
+    double* out = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB;
+    double dsum = 0.0;
+    // thread -> 64 elements: rows warp + 8k (k < 16), columns lane + 32m (m < 4): every warp store is one
+    // 256-byte row segment.  One copy of the interpreter in the instruction stream (no unrolling).
+#pragma unroll 1
+    for (int it = 0; it < 64; it++) {
+      const int r = warp + 8 * (it >> 2), c = lane + 32 * (it & 3);
+      const int gi = ti * NB + r, gj = tj * NB + c;
+      double v;
+      if (gi >= b.N || gj >= b.N) {
+        v = (gi == gj) ? 1.0 : 0.0;
+      } else {
+        v = eval_K(S.P, S.xi + r, S.xj + c, NB);
+        if (gi == gj) { v += diag_add; dsum += v; }
+      }
+      out[(size_t)r * b.Np + c] = v;
+    }
+    if (ti == tj) {
+      S.red[threadIdx.x] = dsum;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int t = 0; t < 256; t++) s += S.red[t];
+        b.diag_part[slot * b.T + ti] = s;
+      }
     }
   }
 }
 
+__global__ void __launch_bounds__(256) interp_grad_kernel(Batch b) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ElemSmem& S = *reinterpret_cast<ElemSmem*>(smem_raw);
+  double* wred = reinterpret_cast<double*>(smem_raw + sizeof(ElemSmem));   // [8][pstride]
+  const int count = b.kcount[CK_GENERIC];
+  const int* list = b.klist + CK_GENERIC * b.list_stride;
+  const int ntiles = tri_count(b.T);
+  const long long nwork = (long long)count * ntiles;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int slot = list[w / ntiles], item = b.ids[slot];
+    if (b.slot_status[slot] != 0) continue;
+    const int tile = (int)(w % ntiles);
+    int ti, tj;
+    tri_decode(tile, ti, tj);
+    __syncthreads();
+    load_program(S.P, b.prog, b.prog_off, b.theta, b.theta_off, item);
+    stage_inputs(S, b, ti, tj);
+    if (threadIdx.x < NB) {
+      S.ai[threadIdx.x] = b.alpha[(size_t)slot * b.Np + ti * NB + threadIdx.x];
+      S.aj[threadIdx.x] = b.alpha[(size_t)slot * b.Np + tj * NB + threadIdx.x];
+    }
+    __syncthreads();
+    const int np = S.P.nparam;
+    double acc[MAX_PARAMS + 1];
+    for (int p = 0; p <= np; p++) acc[p] = 0.0;
+    const double* Kinv = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB;
+    double kv_next = Kinv[(size_t)warp * b.Np + lane];
+#pragma unroll 1
+    for (int it = 0; it < 64; it++) {
+      const int r = warp + 8 * (it >> 2), c = lane + 32 * (it & 3);
+      const double kv = kv_next;
+      if (it + 1 < 64) kv_next = Kinv[(size_t)(warp + 8 * ((it + 1) >> 2)) * b.Np + lane + 32 * ((it + 1) & 3)];
+      const int gi = ti * NB + r, gj = tj * NB + c;
+      if (gi >= b.N || gj >= b.N || gj > gi) continue;
+      double wv = 0.5 * (S.ai[r] * S.aj[c] - kv);
+      if (gi == gj) acc[np] += wv;     // dL/d(noise) = trace(dL/dK)
+      else wv *= 2.0;                  // symmetric pair (i, j) and (j, i)
+      eval_grad(S.P, S.xi + r, S.xj + c, NB, wv, acc, b.quirks);
+    }
+    for (int p = 0; p <= np; p++) {
+      double v = acc[p];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) wred[warp * b.pstride + p] = v;
+    }
+    __syncthreads();
+    double* out = b.grad_part + ((size_t)slot * ntiles + tile) * b.pstride;
+    for (int p = threadIdx.x; p <= np; p += blockDim.x) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) s += wred[q * b.pstride + p];
+      out[p] = s;
+    }
+  }
+}
+
+#ifndef POLY_E4
+#define POLY_E4 2
+#endif
+#ifndef POLY_E8
+#define POLY_E8 1
+#endif
+
 void launch_build_k(const Batch& b, cudaStream_t s) {
-  dim3 grid(tri_count(b.T), b.nslots);
-  build_k_kernel<<<grid, 256, sizeof(ElemSmem), s>>>(b);
-  g_launch_count++;
+  poly_build_kernel<4, POLY_E4><<<g_grid_poly_build[0], 256, sizeof(PolySmem<4>), s>>>(b, CK_POLY4);
+  poly_build_kernel<8, POLY_E8><<<g_grid_poly_build[1], 256, sizeof(PolySmem<8>), s>>>(b, CK_POLY8);
+  interp_build_kernel<<<g_grid_interp_build, 256, sizeof(ElemSmem), s>>>(b);
+  g_launch_count += 3;
+}
+
+void launch_grad(const Batch& b, cudaStream_t s) {
+  poly_grad_kernel<4, POLY_E4><<<g_grid_poly_grad[0], 256, sizeof(PolySmem<4>), s>>>(b, CK_POLY4);
+  poly_grad_kernel<8, POLY_E8><<<g_grid_poly_grad[1], 256, sizeof(PolySmem<8>), s>>>(b, CK_POLY8);
+  const size_t smem = sizeof(ElemSmem) + 8 * (size_t)b.pstride * sizeof(double);
+  interp_grad_kernel<<<g_grid_interp_grad, 256, smem, s>>>(b);
+  g_launch_count += 3;
 }
 
 // Symmetric dense copy of the lower tiles of M1 (for b200gp_build_K / parity tests).
@@ -91,66 +616,6 @@ __global__ void export_sym_kernel(Batch b, double* out) {
 void launch_export_sym(const Batch& b, double* out, cudaStream_t s) {
   dim3 grid(592, b.nslots);
   export_sym_kernel<<<grid, 256, 0, s>>>(b, out);
-  g_launch_count++;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Gradient pass: one CTA per lower tile per slot.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) grad_kernel(Batch b) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  ElemSmem& S = *reinterpret_cast<ElemSmem*>(smem_raw);
-  double* wred = reinterpret_cast<double*>(smem_raw + sizeof(ElemSmem));   // [8][pstride]
-  const int slot = blockIdx.y, item = b.ids[slot];
-  if (b.slot_status[slot] != 0) return;
-  int ti, tj;
-  tri_decode(blockIdx.x, ti, tj);
-  load_program(S.P, b.prog, b.prog_off, b.theta, b.theta_off, item);
-  stage_inputs(S, b, ti, tj);
-  if (threadIdx.x < NB) {
-    S.ai[threadIdx.x] = b.alpha[(size_t)slot * b.Np + ti * NB + threadIdx.x];
-    S.aj[threadIdx.x] = b.alpha[(size_t)slot * b.Np + tj * NB + threadIdx.x];
-  }
-  __syncthreads();
-  const int np = S.P.nparam;
-  double acc[MAX_PARAMS + 1];
-  for (int p = 0; p <= np; p++) acc[p] = 0.0;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const double* Kinv = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB;
-  double kv_next = Kinv[(size_t)warp * b.Np + lane];
-#pragma unroll 1
-  for (int it = 0; it < 64; it++) {
-    const int r = warp + 8 * (it >> 2), c = lane + 32 * (it & 3);
-    const double kv = kv_next;
-    if (it + 1 < 64) kv_next = Kinv[(size_t)(warp + 8 * ((it + 1) >> 2)) * b.Np + lane + 32 * ((it + 1) & 3)];
-    const int gi = ti * NB + r, gj = tj * NB + c;
-    if (gi >= b.N || gj >= b.N || gj > gi) continue;
-    double w = 0.5 * (S.ai[r] * S.aj[c] - kv);
-    if (gi == gj) acc[np] += w;     // dL/d(noise) = trace(dL/dK)
-    else w *= 2.0;                  // symmetric pair (i, j) and (j, i)
-    eval_grad(S.P, S.xi + r, S.xj + c, NB, w, acc, b.quirks);
-  }
-  for (int p = 0; p <= np; p++) {
-    double v = acc[p];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) wred[warp * b.pstride + p] = v;
-  }
-  __syncthreads();
-  double* out = b.grad_part + ((size_t)slot * gridDim.x + blockIdx.x) * b.pstride;
-  for (int p = threadIdx.x; p <= np; p += blockDim.x) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) s += wred[w * b.pstride + p];
-    out[p] = s;
-  }
-}
-
-void launch_grad(const Batch& b, cudaStream_t s) {
-  dim3 grid(tri_count(b.T), b.nslots);
-  const size_t smem = sizeof(ElemSmem) + 8 * (size_t)b.pstride * sizeof(double);
-  grad_kernel<<<grid, 256, smem, s>>>(b);
   g_launch_count++;
 }
 
@@ -225,11 +690,27 @@ void launch_pack_data(const double* X, const double* y, int N, int D, int Np, do
 int configure_chol_kernels();
 int configure_kernels() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(build_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ElemSmem));
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(sizeof(ElemSmem) + 8 * (MAX_PARAMS + 1) * sizeof(double)));
-  if (e != cudaSuccess) return (int)e;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+  struct Cfg { const void* fn; int smem; int* grid; };
+  const int interp_grad_smem = (int)(sizeof(ElemSmem) + 8 * (MAX_PARAMS + 1) * sizeof(double));
+  const Cfg cfgs[] = {
+      {(const void*)poly_build_kernel<4, POLY_E4>, (int)sizeof(PolySmem<4>), &g_grid_poly_build[0]},
+      {(const void*)poly_build_kernel<8, POLY_E8>, (int)sizeof(PolySmem<8>), &g_grid_poly_build[1]},
+      {(const void*)poly_grad_kernel<4, POLY_E4>, (int)sizeof(PolySmem<4>), &g_grid_poly_grad[0]},
+      {(const void*)poly_grad_kernel<8, POLY_E8>, (int)sizeof(PolySmem<8>), &g_grid_poly_grad[1]},
+      {(const void*)interp_build_kernel, (int)sizeof(ElemSmem), &g_grid_interp_build},
+      {(const void*)interp_grad_kernel, interp_grad_smem, &g_grid_interp_grad},
+  };
+  for (const Cfg& c : cfgs) {
+    e = cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c.fn, 256, c.smem);
+    if (e != cudaSuccess) return (int)e;
+    *c.grid = g_sm_count * (per_sm > 0 ? per_sm : 1);
+  }
   return configure_chol_kernels();
 }
 

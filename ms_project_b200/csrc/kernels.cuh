@@ -1,6 +1,7 @@
 // Internal launch interface between the C-ABI layer (api.cu) and the kernel translation units.
 #pragma once
 #include "common.cuh"
+#include "cprog.cuh"
 
 namespace b200gp {
 
@@ -38,6 +39,11 @@ struct Batch {
   int try_no;                // ladder step of this pipeline run (0 = plain)
   int quirks;
   int add_diag;              // 1: add noise + 1e-8 + jitter to the diagonal (K_y); 0: bare kern.K
+  // compiled programs of this chunk (cprog.cuh), written by launch_compile
+  CProg* cprog;              // [slot]
+  int* klist;                // [CK_KINDS][list_stride] slots of each kind, in slot order
+  int* kcount;               // [CK_KINDS]
+  int list_stride;
 };
 
 enum GemmMode : int { GM_TRSM = 0, GM_VTRSM = 3, GM_KINV = 4, GM_UPD = 5, GM_VUPD = 6 };
@@ -47,6 +53,7 @@ struct UpdRange { int k0, kw, j0, j1; };
 // GM_VUPD (right-looking L^-T): S_jm (+)= sum_{i in [max(j,k0), k0+kw)} V_ji L_mi^T for columns m in [j0, j1), rows
 // j < k0+kw; a tile is overwritten when its first contribution arrives (j >= k0), accumulated afterwards.
 
+void launch_compile(const Batch& b, cudaStream_t s);                        // programs -> CProg + per-kind slot lists
 void launch_build_k(const Batch& b, cudaStream_t s);
 void launch_export_sym(const Batch& b, double* out, cudaStream_t s);       // out[slot][N][N] symmetric copy of M1
 void launch_potrf_diag(const Batch& b, int k, cudaStream_t s);

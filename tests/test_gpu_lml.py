@@ -11,7 +11,11 @@ from conftest import to_oracle_expr, from_string, make_data
 pytestmark = pytest.mark.gpu
 
 KERNELS = ['SE_1', 'RQ_1', 'PER_1', 'LIN_1', 'SE_1 + RQ_2', 'SE_1 * PER_1 + RQ_2', '(SE_1 + RQ_2) * LIN_2',
-           'SE_1 * SE_2 * RQ_1 + PER_2 * LIN_1 + CONST_1', 'LIN_1 * LIN_1 * PER_1', '(SE_1 + PER_2) * (RQ_1 + LIN_2)']
+           'SE_1 * SE_2 * RQ_1 + PER_2 * LIN_1 + CONST_1', 'LIN_1 * LIN_1 * PER_1', '(SE_1 + PER_2) * (RQ_1 + LIN_2)',
+           # 5-8 leaves: register-resident polynomial form with 8 leaf slots
+           '(SE_1 + RQ_2) * (PER_1 + LIN_2 + SE_2) * RQ_1', 'SE_1 * RQ_2 + PER_1 * LIN_2 + SE_2 * PER_2 + RQ_1 + LIN_1',
+           # 9 leaves / 27 product terms: falls back to the postfix interpreter
+           '(SE_1 + RQ_1 + PER_1) * (SE_2 + RQ_2 + LIN_2) * (PER_2 + LIN_1 + SE_2)']
 
 
 def random_theta(batch, rng, lo=-0.7, hi=0.7):
@@ -27,7 +31,7 @@ def test_lml_grad_matches_oracle(engine, n, d):
     X, y = make_data(n, d, seed=n)
     kernels = [from_string(s) for s in KERNELS]
     batch = ProgramBatch(kernels)
-    engine.bind(X, y, slots=4, max_params=batch.max_params)     # 4 slots < 10 items: exercises chunking
+    engine.bind(X, y, slots=4, max_params=batch.max_params)     # 4 slots < 13 items: exercises chunking
     engine.upload_programs(batch)
     theta, ks, nz = random_theta(batch, np.random.RandomState(1))
     lml, dlml, status, tries = engine.lml_grad(batch, theta)
