@@ -1,33 +1,38 @@
-// 128x128 FP64 tile GEMM on the DMMA tensor pipe:  acc(128x128) += A(128 x K) * B(128 x K)^T
+// 128x64 FP64 tile GEMM on the DMMA tensor pipe:  acc(128x64) += A(128 x K) * B(64 x K)^T
 //
 // Both operands are row-major with K contiguous ("NT"), which is how every blocked phase of the
 // Cholesky / inverse is arranged (see chol_kernels.cu).  Blackwell's tcgen05/UMMA has no FP64 kind;
 // the FP64 tensor path on sm_100a is `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4, measured 36.9 TFLOP/s
-// register-resident, profiles/fp64_peaks_r01.json), so this is a warp-level MMA kernel:
-//   * TG_WM x TG_WN warps (default 4 x 4 = 512 threads), warp tile (128/TG_WM) x 32 DMMA m8n8 tiles
-//   * operands stream global -> shared through a 4-stage cp.async (LDGSTS) ring, 16 doubles of K
-//     per stage, rows padded to 20 doubles so the 64-bit fragment loads are bank-conflict free
-//   * one __syncthreads per stage
-//   * [kc_lo, kc_hi): per-warp range of K-chunks that can contribute (triangular operands / diagonal output tiles);
-//     outside it the warp still takes part in the copies and barriers but issues no DMMA
+// register-resident, profiles/fp64_peaks_r01.json), so this is a warp-level MMA kernel.  The shape was
+// chosen from measurements (tools/gemm_probe.cu, profiles/gemm_probe_r01.txt):
+//   * 4 x 2 warps (256 threads), warp tile 32 x 32 = 4 x 4 DMMA m8n8 tiles, TWO CTAs per SM (<= 128 registers,
+//     90 KB shared memory each): while one CTA sits in its chunk barrier, tile prologue or epilogue, the other
+//     keeps the tensor pipe fed
+//   * operands stream global -> shared through a 3-stage cp.async (LDGSTS) ring, 16 doubles of K per stage,
+//     rows padded to 20 doubles so the 64-bit fragment loads are bank-conflict free
+//   * SKEWED chunk barrier: the one __syncthreads per chunk sits in front of the chunk's LAST k-step, whose
+//     fragments are already in registers, and the first fragments of the next chunk are fetched right behind it,
+//     so 16 DMMAs per warp are queued while the block re-synchronises (+15 % over a barrier at the chunk head)
+//   * [kc_lo, kc_hi): per-warp range of K-chunks that can contribute (triangular operands / diagonal output
+//     tiles); outside it the warp still takes part in the copies and barriers but issues no DMMA
 #pragma once
 #include "common.cuh"
 
 namespace b200gp {
 
-#ifndef TG_WARPS_M
-#define TG_WARPS_M 4
-#endif
-constexpr int TG_WM = TG_WARPS_M;         // warps along M
-constexpr int TG_WN = 4;                  // warps along N
+constexpr int TG_WM = 4;                  // warps along M
+constexpr int TG_WN = 2;                  // warps along N
 constexpr int TG_THREADS = 32 * TG_WM * TG_WN;
-constexpr int TG_MT = NB / TG_WM / 8;     // DMMA m-tiles per warp
-constexpr int TG_NT = NB / TG_WN / 8;     // DMMA n-tiles per warp
+constexpr int TG_TM = 32 * TG_WM;         // 128 = NB rows of C per CTA
+constexpr int TG_TN = 32 * TG_WN;         // 64 columns of C per CTA (half a tile)
+constexpr int TG_MT = 4;                  // DMMA m-tiles per warp
+constexpr int TG_NT = 4;                  // DMMA n-tiles per warp
 constexpr int TG_KC = 16;                 // K elements per pipeline stage
 constexpr int TG_LDK = TG_KC + 4;         // padded row length in shared memory (doubles)
-constexpr int TG_STAGES = 4;
-constexpr int TG_STAGE_DOUBLES = 2 * NB * TG_LDK;                       // A + B per stage
-constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_DOUBLES * 8;         // 163,840 B
+constexpr int TG_STAGES = 3;
+constexpr int TG_STAGE_DOUBLES = (TG_TM + TG_TN) * TG_LDK;              // A + B per stage
+constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_DOUBLES * 8;         // 92,160 B -> two CTAs per SM
+static_assert(TG_TM == NB && 2 * TG_TN == NB, "a 128x128 tile is two CTA tiles side by side");
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -37,12 +42,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// Warp -> (wm, wn) position in the TG_WM x TG_WN warp grid.  A warp lives on SM sub-partition (warp % 4); the columns
-// are rotated against the rows so every sub-partition hosts one warp of EACH wn and of each wm.  The structural-zero
-// skips below (which depend on wn, on wm, or on wn > wm) then shorten all four DMMA pipes evenly.
+// Warp -> (wm, wn) position in the 4 x 2 warp grid.  A warp lives on SM sub-partition (warp % 4); sub-partition s
+// hosts the warps (wm = s, wn = 0) and (wm = 3 - s, wn = 1), so the structural-zero skips (which grow with wm, shrink
+// with wn) shorten all four DMMA pipes about evenly.
 __device__ __forceinline__ void warp_coords(int warp, int& wm, int& wn) {
-  wm = warp / TG_WN;
-  wn = (warp - wm) & (TG_WN - 1);
+  const int s = warp & 3;
+  wn = warp >> 2;
+  wm = wn ? 3 - s : s;
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -50,23 +56,28 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// Issue the cp.async copies of one K-chunk (A rows and B rows, 128 x 16 doubles each).
+// Issue the cp.async copies of one K-chunk (128 A rows and 64 B rows, 16 doubles each).
 __device__ __forceinline__ void tg_load_stage(double* stage, const double* __restrict__ A, size_t lda,
                                               const double* __restrict__ B, size_t ldb, int koff) {
   double* As = stage;
-  double* Bs = stage + NB * TG_LDK;
+  double* Bs = stage + TG_TM * TG_LDK;
 #pragma unroll
-  for (int r = 0; r < 1024 / TG_THREADS; r++) {
-    const int seg = threadIdx.x + TG_THREADS * r;   // 1024 16-byte segments per operand
+  for (int r = 0; r < TG_TM * 8 / TG_THREADS; r++) {
+    const int seg = threadIdx.x + TG_THREADS * r;   // 8 16-byte segments per row
     const int row = seg >> 3, part = (seg & 7) * 2;
     cp_async16(As + row * TG_LDK + part, A + (size_t)row * lda + koff + part);
+  }
+#pragma unroll
+  for (int r = 0; r < TG_TN * 8 / TG_THREADS; r++) {
+    const int seg = threadIdx.x + TG_THREADS * r;
+    const int row = seg >> 3, part = (seg & 7) * 2;
     cp_async16(Bs + row * TG_LDK + part, B + (size_t)row * ldb + koff + part);
   }
 }
 
-// acc[mt][nt][2]: C fragment of DMMA tile (mt, nt) of this warp's (8 TG_MT) x (8 TG_NT) sub-tile.
+// acc[mt][nt][2]: C fragment of DMMA tile (mt, nt) of this warp's 32 x 32 sub-tile.
 // Element (row, col) of the CTA tile held in acc[mt][nt][e]:
-//   row = wm*8*TG_MT + mt*8 + (lane>>2),  col = wn*8*TG_NT + nt*8 + (lane&3)*2 + e
+//   row = wm*32 + mt*8 + (lane>>2),  col = wn*32 + nt*8 + (lane&3)*2 + e
 __device__ __forceinline__ void tile_gemm_nt(double (&acc)[TG_MT][TG_NT][2], const double* __restrict__ A, size_t lda,
                                              const double* __restrict__ B, size_t ldb, int nchunks, double* smem,
                                              int kc_lo = 0, int kc_hi = 1 << 30) {
@@ -74,38 +85,62 @@ __device__ __forceinline__ void tile_gemm_nt(double (&acc)[TG_MT][TG_NT][2], con
   int wm, wn;
   warp_coords(warp, wm, wn);
   const int g = lane >> 2, tg = lane & 3;
+  const int aoff = (wm * 32 + g) * TG_LDK + tg;
+  const int boff = TG_TM * TG_LDK + (wn * 32 + g) * TG_LDK + tg;
 
 #pragma unroll
   for (int s = 0; s < TG_STAGES - 1; s++) {
     if (s < nchunks) tg_load_stage(smem + s * TG_STAGE_DOUBLES, A, lda, B, ldb, s * TG_KC);
     cp_async_commit();
   }
+  cp_async_wait<TG_STAGES - 2>();
+  __syncthreads();
+  double a[TG_MT], b[TG_NT];
+#pragma unroll
+  for (int mt = 0; mt < TG_MT; mt++) a[mt] = smem[aoff + mt * 8 * TG_LDK];
+#pragma unroll
+  for (int nt = 0; nt < TG_NT; nt++) b[nt] = smem[boff + nt * 8 * TG_LDK];
+
   for (int kc = 0; kc < nchunks; kc++) {
-    cp_async_wait<TG_STAGES - 2>();
-    __syncthreads();
-    {
+    {   // refill the stage chunk kc-1 was read from: every warp passed the barrier of the previous iteration
       const int nk = kc + TG_STAGES - 1;
       if (nk < nchunks) tg_load_stage(smem + (nk % TG_STAGES) * TG_STAGE_DOUBLES, A, lda, B, ldb, nk * TG_KC);
       cp_async_commit();
     }
-    const double* As = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + (wm * 8 * TG_MT + g) * TG_LDK + tg;
-    const double* Bs = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + NB * TG_LDK + (wn * 8 * TG_NT + g) * TG_LDK + tg;
-    if (kc < kc_lo || kc >= kc_hi) continue;     // warp-uniform: this warp's operands are structurally zero here
+    const double* As = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + aoff;
+    const double* Bs = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + boff;
+    const double* An = smem + ((kc + 1) % TG_STAGES) * TG_STAGE_DOUBLES + aoff;
+    const double* Bn = smem + ((kc + 1) % TG_STAGES) * TG_STAGE_DOUBLES + boff;
+    const bool act = (kc >= kc_lo) && (kc < kc_hi);   // warp-uniform: otherwise the operands are structurally zero
 #pragma unroll
     for (int kk = 0; kk < TG_KC; kk += 4) {
-      double a[TG_MT], b[TG_NT];
+      double a2[TG_MT], b2[TG_NT];
+      if (kk + 4 < TG_KC) {
 #pragma unroll
-      for (int mt = 0; mt < TG_MT; mt++) a[mt] = As[mt * 8 * TG_LDK + kk];
+        for (int mt = 0; mt < TG_MT; mt++) a2[mt] = As[mt * 8 * TG_LDK + kk + 4];
 #pragma unroll
-      for (int nt = 0; nt < TG_NT; nt++) b[nt] = Bs[nt * 8 * TG_LDK + kk];
+        for (int nt = 0; nt < TG_NT; nt++) b2[nt] = Bs[nt * 8 * TG_LDK + kk + 4];
+      } else {
+        cp_async_wait<TG_STAGES - 2>();     // chunk kc+1 has landed (this thread's copies) ...
+        __syncthreads();                    // ... for every thread, and every warp is done reading chunk kc
 #pragma unroll
-      for (int mt = 0; mt < TG_MT; mt++)
+        for (int mt = 0; mt < TG_MT; mt++) a2[mt] = An[mt * 8 * TG_LDK];
 #pragma unroll
-        for (int nt = 0; nt < TG_NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        for (int nt = 0; nt < TG_NT; nt++) b2[nt] = Bn[nt * 8 * TG_LDK];
+      }
+      if (act) {
+#pragma unroll
+        for (int mt = 0; mt < TG_MT; mt++)
+#pragma unroll
+          for (int nt = 0; nt < TG_NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < TG_MT; mt++) a[mt] = a2[mt];
+#pragma unroll
+      for (int nt = 0; nt < TG_NT; nt++) b[nt] = b2[nt];
     }
   }
   cp_async_wait<0>();
-  __syncthreads();
 }
 
 }  // namespace b200gp
