@@ -14,6 +14,8 @@
 #include "kernels.cuh"
 #include "kprog.cuh"
 #include "cprog.cuh"
+#include "fastmath.cuh"
+#include <cstddef>
 
 namespace b200gp {
 
@@ -117,6 +119,25 @@ struct PolySmem {
   double noise;
 };
 
+// Explicit shared-window loads: the hot loops address PolySmem by 32-bit offsets from one base register instead of
+// generic pointers (which cost a S2UR / ULEA window-base sequence per access on sm_100).
+__device__ __forceinline__ double lds_f64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void lds_v2(unsigned a, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+template <int E>
+__device__ __forceinline__ void lds_rows(unsigned a, double (&v)[E]) {      // E consecutive doubles, 16-byte aligned for E = 2
+  if (E == 2) lds_v2(a, v[0], v[E - 1]);
+  else {
+#pragma unroll
+    for (int e = 0; e < E; e++) v[e] = lds_f64(a + 8 * e);
+  }
+}
+
 __device__ __forceinline__ void leaf_constants(int op, const double* __restrict__ th, double* cst, double& ivar) {
   double c0 = th[0], c1 = 0, c2 = 0, c3 = 0;
   switch (op) {
@@ -137,121 +158,111 @@ __device__ __forceinline__ void point_values(int op, const double* cst, double x
   else A = x;
 }
 
-// Leaf values for E rows of one column.  aux keeps what the reverse sweep cannot cheaply recompute.
+// Leaf values for E rows of one column.  `cst`, `srow`, `crow` are shared-window addresses (leaf constants, PER
+// sin / cos rows); aux keeps what the reverse sweep cannot cheaply recompute.  Straight-line math (fastmath.cuh) so
+// the E chains interleave.
 template <int E>
-__device__ __forceinline__ void leaf_fwd(int op, const double* cst, const double* Ar, const double* Sr, const double* Cr,
+__device__ __forceinline__ void leaf_fwd(int op, unsigned cst, const double (&Ar)[E], unsigned srow, unsigned crow,
                                          double Aj, double Sj, double Cj, double (&v)[E], double (&aux)[E]) {
-  const double c0 = cst[0];
-  switch (op) {
-    case OP_SE: {        // rbf.ipynb#1-2: v exp(-r^2 / 2)
-      const double c1 = cst[1];
+  double c0, c1;
+  lds_v2(cst, c0, c1);
+  if (op == OP_SE) {            // rbf.ipynb#1-2: v exp(-r^2 / 2)
 #pragma unroll
-      for (int e = 0; e < E; e++) { const double r = (Ar[e] - Aj) * c1; const double a = r * r; aux[e] = a; v[e] = c0 * exp(-0.5 * a); }
-      break;
-    }
-    case OP_RQ: {        // rational-quadratic.ipynb#2: v exp(-a log1p(r^2 / 2a))
-      const double c1 = cst[1], c2 = cst[2], c3 = cst[3];
+    for (int e = 0; e < E; e++) { const double r = (Ar[e] - Aj) * c1; const double a = r * r; aux[e] = a; v[e] = c0 * exp_sl(-0.5 * a); }
+  } else if (op == OP_RQ) {     // rational-quadratic.ipynb#2: v exp(-a log1p(r^2 / 2a))
+    double c2, c3;
+    lds_v2(cst + 16, c2, c3);
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        const double r = (Ar[e] - Aj) * c1;
-        const double lg = log1p((r * r) * c3);
-        aux[e] = lg;
-        v[e] = c0 * exp(-c2 * lg);
-      }
-      break;
+    for (int e = 0; e < E; e++) {
+      const double r = (Ar[e] - Aj) * c1;
+      const double lg = log1p_pos((r * r) * c3);
+      aux[e] = lg;
+      v[e] = c0 * exp_sl(-c2 * lg);
     }
-    case OP_PER: {       // periodic.ipynb#2: v exp(-2 sin^2(pi (x - x') / p) / l^2), sin(a_i - a_j) by the angle-difference identity
-      const double il = cst[2];
+  } else if (op == OP_PER) {    // periodic.ipynb#2: v exp(-2 sin^2(pi (x - x') / p) / l^2); sin(a_i - a_j) by the angle-difference identity
+    const double il = lds_f64(cst + 16);
+    double Sr[E], Cr[E];
+    lds_rows<E>(srow, Sr);
+    lds_rows<E>(crow, Cr);
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        const double s = Sr[e] * Cj - Cr[e] * Sj;
-        const double q = s * il;
-        aux[e] = s;
-        v[e] = c0 * exp(-2.0 * (q * q));
-      }
-      break;
+    for (int e = 0; e < E; e++) {
+      const double s = Sr[e] * Cj - Cr[e] * Sj;
+      const double q = s * il;
+      aux[e] = s;
+      v[e] = c0 * exp_sl(-2.0 * (q * q));
     }
-    case OP_LIN: {       // linear.ipynb#2: v (x - c)(x' - c)
+  } else if (op == OP_LIN) {    // linear.ipynb#2: v (x - c)(x' - c)
 #pragma unroll
-      for (int e = 0; e < E; e++) { aux[e] = Ar[e] * Aj; v[e] = c0 * aux[e]; }
-      break;
-    }
-    default: {
+    for (int e = 0; e < E; e++) { aux[e] = Ar[e] * Aj; v[e] = c0 * aux[e]; }
+  } else {
 #pragma unroll
-      for (int e = 0; e < E; e++) { aux[e] = 0.0; v[e] = c0; }
-      break;
-    }
+    for (int e = 0; e < E; e++) { aux[e] = 0.0; v[e] = c0; }
   }
 }
 
 // acc[p] += sum_e g[e] dv/dtheta_p for the leaf's own parameters (same formulas as kprog.cuh eval_grad).
 template <int E>
-__device__ __forceinline__ void leaf_bwd(int op, const double* cst, double ivar, const double* Ar, const double* Sr,
-                                         const double* Cr, double Aj, double Sj, double Cj, const double (&g)[E],
-                                         const double (&v)[E], const double (&aux)[E], double (&acc)[3], int quirks) {
-  switch (op) {
-    case OP_SE: {
-      const double c1 = cst[1];
+__device__ __forceinline__ void leaf_bwd(int op, unsigned cst, double ivar, const double (&Ar)[E], unsigned srow, unsigned crow,
+                                         double Aj, double Sj, double Cj, const double (&g)[E], const double (&v)[E],
+                                         const double (&aux)[E], double (&acc)[3], int quirks) {
+  if (op == OP_SE) {
+    const double c1 = lds_f64(cst + 8);
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        const double gv = g[e] * v[e];
-        acc[0] = fma(gv, ivar, acc[0]);
-        acc[1] = fma(gv, aux[e] * c1, acc[1]);
-      }
-      break;
+    for (int e = 0; e < E; e++) {
+      const double gv = g[e] * v[e];
+      acc[0] = fma(gv, ivar, acc[0]);
+      acc[1] = fma(gv, aux[e] * c1, acc[1]);
     }
-    case OP_RQ: {
-      const double c1 = cst[1], c2 = cst[2], c3 = cst[3];
+  } else if (op == OP_RQ) {
+    const double c1 = lds_f64(cst + 8);
+    double c2, c3;
+    lds_v2(cst + 16, c2, c3);
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        const double r = (Ar[e] - Aj) * c1;
-        const double u = (r * r) * c3;
-        const double e1 = 1.0 / (1.0 + u);
-        const double gv = g[e] * v[e];
-        acc[0] = fma(gv, ivar, acc[0]);
-        acc[1] = fma(gv, (u * (2.0 * c2)) * c1 * e1, acc[1]);
-        acc[2] = fma(gv, u * e1 - aux[e], acc[2]);
-      }
-      break;
+    for (int e = 0; e < E; e++) {
+      const double r = (Ar[e] - Aj) * c1;
+      const double u = (r * r) * c3;
+      const double e1 = rcp_sl(1.0 + u);
+      const double gv = g[e] * v[e];
+      acc[0] = fma(gv, ivar, acc[0]);
+      acc[1] = fma(gv, (u * (2.0 * c2)) * c1 * e1, acc[1]);
+      acc[2] = fma(gv, u * e1 - aux[e], acc[2]);
     }
-    case OP_PER: {
-      const double il = cst[2], ip = cst[3];
-      const double lsf = (quirks & QUIRK_PER_LENGTHSCALE) ? 1.0 : 4.0;
+  } else if (op == OP_PER) {
+    double il, ip;
+    lds_v2(cst + 16, il, ip);
+    const double lsf = (quirks & QUIRK_PER_LENGTHSCALE) ? 1.0 : 4.0;
+    double Sr[E], Cr[E];
+    lds_rows<E>(srow, Sr);
+    lds_rows<E>(crow, Cr);
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        const double s = aux[e];
-        const double c = Cr[e] * Cj + Sr[e] * Sj;
-        const double base = Ar[e] - Aj;
-        const double q = s * il;
-        const double gv = g[e] * v[e];
-        acc[0] = fma(gv, ivar, acc[0]);
-        acc[1] = fma(gv, (4.0 * il * il) * s * c * (base * ip), acc[1]);
-        acc[2] = fma(gv, lsf * (q * q) * il, acc[2]);
-      }
-      break;
+    for (int e = 0; e < E; e++) {
+      const double s = aux[e];
+      const double c = Cr[e] * Cj + Sr[e] * Sj;
+      const double base = Ar[e] - Aj;
+      const double q = s * il;
+      const double gv = g[e] * v[e];
+      acc[0] = fma(gv, ivar, acc[0]);
+      acc[1] = fma(gv, (4.0 * il * il) * s * c * (base * ip), acc[1]);
+      acc[2] = fma(gv, lsf * (q * q) * il, acc[2]);
     }
-    case OP_LIN: {
-      const double sf = (quirks & QUIRK_LIN_SHIFT) ? 1.0 : cst[0];
+  } else if (op == OP_LIN) {
+    const double sf = (quirks & QUIRK_LIN_SHIFT) ? 1.0 : lds_f64(cst);
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        acc[0] = fma(g[e], aux[e], acc[0]);
-        acc[1] = fma(g[e], sf * (-(Ar[e] + Aj)), acc[1]);
-      }
-      break;
+    for (int e = 0; e < E; e++) {
+      acc[0] = fma(g[e], aux[e], acc[0]);
+      acc[1] = fma(g[e], sf * (-(Ar[e] + Aj)), acc[1]);
     }
-    default: {
+  } else {
 #pragma unroll
-      for (int e = 0; e < E; e++) acc[0] += g[e];
-      break;
-    }
+    for (int e = 0; e < E; e++) acc[0] += g[e];
   }
 }
 
 // Cooperative prologue of one (slot, tile) work item: program, leaf constants, row-side tables; returns the
-// column-side values of this thread's column in registers.
+// column-side values of this thread's column and the leaf opcodes in registers.
 template <int LMAX>
 __device__ __forceinline__ void poly_prologue(PolySmem<LMAX>& S, const Batch& b, int slot, int ti, int tj,
-                                              double (&Aj)[LMAX], double (&Sj)[LMAX], double (&Cj)[LMAX]) {
+                                              double (&Aj)[LMAX], double (&Sj)[LMAX], double (&Cj)[LMAX], int (&ops)[LMAX]) {
   __syncthreads();                                           // the previous work item is done with S
   if (threadIdx.x < (int)(sizeof(CProg) / 4))
     reinterpret_cast<int*>(&S.cp)[threadIdx.x] = reinterpret_cast<const int*>(&b.cprog[slot])[threadIdx.x];
@@ -276,17 +287,30 @@ __device__ __forceinline__ void poly_prologue(PolySmem<LMAX>& S, const Batch& b,
 #pragma unroll
   for (int l = 0; l < LMAX; l++) {
     Aj[l] = 0.0; Sj[l] = 0.0; Cj[l] = 0.0;
+    ops[l] = OP_CONST;
     if (l < L) {
       const int4 lf = S.cp.leaf[l];
+      ops[l] = lf.x;
       point_values(lf.x, S.cst[l], b.Xt[(size_t)lf.y * b.Np + tj * NB + c], Aj[l], Sj[l], Cj[l]);
     }
   }
 }
 
+// product-term masks: 4 leaf slots expand to at most 4 terms (one register); 8 slots read shared memory
+template <int LMAX>
+__device__ __forceinline__ unsigned term_mask(unsigned terms4, unsigned term_addr, int g) {
+  if (LMAX == 4) return (terms4 >> (8 * g)) & 0xffu;
+  unsigned m;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(m) : "r"(term_addr + g));
+  return m;
+}
+
 template <int LMAX, int E>
 __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_build_kernel(Batch b, int kind) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PolySmem<LMAX>& S = *reinterpret_cast<PolySmem<LMAX>*>(smem_raw);
+  typedef PolySmem<LMAX> SM;
+  SM& S = *reinterpret_cast<SM*>(smem_raw);
+  const unsigned sb = (unsigned)__cvta_generic_to_shared(smem_raw);
   const int count = b.kcount[kind];
   const int* list = b.klist + kind * b.list_stride;
   const int ntiles = tri_count(b.T);
@@ -297,9 +321,11 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_build_kernel(Batc
     int ti, tj;
     tri_decode((int)(w % ntiles), ti, tj);
     double Aj[LMAX], Sj[LMAX], Cj[LMAX];
-    poly_prologue<LMAX>(S, b, slot, ti, tj, Aj, Sj, Cj);
+    int ops[LMAX];
+    poly_prologue<LMAX>(S, b, slot, ti, tj, Aj, Sj, Cj, ops);
     __syncthreads();
     const int L = S.cp.L, G = S.cp.G;
+    const unsigned terms4 = *reinterpret_cast<const unsigned*>(S.cp.term);
     const double diag_add = b.add_diag ? S.noise + EXACT_INFERENCE_JITTER + (b.jitter ? b.jitter[slot] : 0.0) : 0.0;
     double* out = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB + c;
     const int gj = tj * NB + c;
@@ -308,12 +334,17 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_build_kernel(Batc
       double v[LMAX][E], aux[E];
 #pragma unroll
       for (int l = 0; l < LMAX; l++)
-        if (l < L) leaf_fwd<E>(S.cp.leaf[l].x, S.cst[l], &S.Ai[l][r0], &S.Si[l][r0], &S.Ci[l][r0], Aj[l], Sj[l], Cj[l], v[l], aux);
+        if (l < L) {
+          double Ar[E];
+          lds_rows<E>(sb + (unsigned)offsetof(SM, Ai) + (l * NB + r0) * 8, Ar);
+          leaf_fwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, Ar, sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8,
+                      sb + (unsigned)offsetof(SM, Ci) + (l * NB + r0) * 8, Aj[l], Sj[l], Cj[l], v[l], aux);
+        }
       double k[E];
 #pragma unroll
       for (int e = 0; e < E; e++) k[e] = 0.0;
       for (int g = 0; g < G; g++) {
-        const unsigned mask = S.cp.term[g];
+        const unsigned mask = term_mask<LMAX>(terms4, sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), g);
         double p[E];
 #pragma unroll
         for (int e = 0; e < E; e++) p[e] = 1.0;
@@ -350,7 +381,9 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_build_kernel(Batc
 template <int LMAX, int E>
 __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_grad_kernel(Batch b, int kind) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PolySmem<LMAX>& S = *reinterpret_cast<PolySmem<LMAX>*>(smem_raw);
+  typedef PolySmem<LMAX> SM;
+  SM& S = *reinterpret_cast<SM*>(smem_raw);
+  const unsigned sb = (unsigned)__cvta_generic_to_shared(smem_raw);
   constexpr int NV = 3 * LMAX + 1;
   const int count = b.kcount[kind];
   const int* list = b.klist + kind * b.list_stride;
@@ -365,11 +398,13 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_grad_kernel(Batch
     int ti, tj;
     tri_decode(tile, ti, tj);
     double Aj[LMAX], Sj[LMAX], Cj[LMAX];
-    poly_prologue<LMAX>(S, b, slot, ti, tj, Aj, Sj, Cj);
+    int ops[LMAX];
+    poly_prologue<LMAX>(S, b, slot, ti, tj, Aj, Sj, Cj, ops);
     if (threadIdx.x >= NB) S.ai[c] = b.alpha[(size_t)slot * b.Np + ti * NB + c];
     const double aj = b.alpha[(size_t)slot * b.Np + tj * NB + c];
     __syncthreads();
     const int L = S.cp.L, G = S.cp.G, single = S.cp.single;
+    const unsigned terms4 = *reinterpret_cast<const unsigned*>(S.cp.term);
     double acc[LMAX][3], accn = 0.0;
 #pragma unroll
     for (int l = 0; l < LMAX; l++) { acc[l][0] = 0.0; acc[l][1] = 0.0; acc[l][2] = 0.0; }
@@ -384,11 +419,12 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_grad_kernel(Batch
     for (int e = 0; e < E; e++) kv[e] = (rbeg < rend) ? Kinv[(size_t)(rbeg + e) * b.Np] : 0.0;
 #pragma unroll 1
     for (int r0 = rbeg; r0 < rend; r0 += E) {
-      double wt[E];
+      double wt[E], ar[E];
+      lds_rows<E>(sb + (unsigned)offsetof(SM, ai) + r0 * 8, ar);
 #pragma unroll
       for (int e = 0; e < E; e++) {
         const int gi = ti * NB + r0 + e;
-        double wv = 0.5 * (S.ai[r0 + e] * aj - kv[e]);
+        double wv = 0.5 * (ar[e] * aj - kv[e]);
         const bool valid = gi < b.N && gj <= gi;       // gj <= gi < N
         if (gi == gj) { if (valid) accn += wv; } else wv *= 2.0;      // symmetric pair (i, j), (j, i)
         wt[e] = valid ? wv : 0.0;
@@ -400,7 +436,12 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_grad_kernel(Batch
       double v[LMAX][E], aux[LMAX][E];
 #pragma unroll
       for (int l = 0; l < LMAX; l++)
-        if (l < L) leaf_fwd<E>(S.cp.leaf[l].x, S.cst[l], &S.Ai[l][r0], &S.Si[l][r0], &S.Ci[l][r0], Aj[l], Sj[l], Cj[l], v[l], aux[l]);
+        if (l < L) {
+          double Ar[E];
+          lds_rows<E>(sb + (unsigned)offsetof(SM, Ai) + (l * NB + r0) * 8, Ar);
+          leaf_fwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, Ar, sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8,
+                      sb + (unsigned)offsetof(SM, Ci) + (l * NB + r0) * 8, Aj[l], Sj[l], Cj[l], v[l], aux[l]);
+        }
 #pragma unroll
       for (int l = 0; l < LMAX; l++)
         if (l < L) {
@@ -413,7 +454,7 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_grad_kernel(Batch
 #pragma unroll
             for (int e = 0; e < E; e++) adj[e] = 0.0;
             for (int t = 0; t < G; t++) {
-              const unsigned mask = S.cp.term[t];
+              const unsigned mask = term_mask<LMAX>(terms4, sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), t);
               if (!(mask & (1u << l))) continue;
               double p[E];
 #pragma unroll
@@ -430,8 +471,11 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_grad_kernel(Batch
 #pragma unroll
             for (int e = 0; e < E; e++) g[e] = wt[e] * adj[e];
           }
-          leaf_bwd<E>(S.cp.leaf[l].x, S.cst[l], S.ivar[l], &S.Ai[l][r0], &S.Si[l][r0], &S.Ci[l][r0], Aj[l], Sj[l], Cj[l], g,
-                      v[l], aux[l], acc[l], b.quirks);
+          double Ar[E];
+          lds_rows<E>(sb + (unsigned)offsetof(SM, Ai) + (l * NB + r0) * 8, Ar);
+          leaf_bwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, lds_f64(sb + (unsigned)offsetof(SM, ivar) + l * 8), Ar,
+                      sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8, sb + (unsigned)offsetof(SM, Ci) + (l * NB + r0) * 8,
+                      Aj[l], Sj[l], Cj[l], g, v[l], aux[l], acc[l], b.quirks);
         }
     }
     // CTA reduction in a fixed order: lanes (shuffle tree), then the 8 warps

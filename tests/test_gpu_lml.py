@@ -60,6 +60,27 @@ def test_kernel_matrix_matches_oracle_and_gpml(engine):
         assert np.allclose(K, ok.K(ok.parse(case['kernel']), case['theta'], X), rtol=1e-13, atol=1e-13)
 
 
+def test_extreme_hyperparameters(engine):
+    """Lengthscales / periods far outside the data scale (line-search excursions of L-BFGS-B reach them): the
+    straight-line exp / log1p of csrc/fastmath.cuh must flush, not wrap (exponent arguments down to -1e20)."""
+    from ms_project_b200.program import ProgramBatch
+    from oracle import kernels as ok
+    X, _ = make_data(140, 1, seed=2)
+    cases = [('SE_1', [1.3, 1e-10]), ('SE_1', [2.0, 3e-4]), ('SE_1', [0.5, 1e6]), ('RQ_1', [1.1, 1e-9, 0.7]),
+             ('RQ_1', [1.1, 2e-3, 40.0]), ('RQ_1', [0.9, 1e5, 1e-3]), ('PER_1', [1.2, 0.37, 1e-9]), ('PER_1', [1.2, 1e-3, 0.4]),
+             ('PER_1', [0.8, 50.0, 1e-4]), ('SE_1 * PER_1 + RQ_1', [1.0, 1e-7, 1.0, 2.0, 1e-8, 1.0, 1e-6, 3.0])]
+    for name, th in cases:
+        k = from_string(name)
+        batch = ProgramBatch([k])
+        engine.bind(X, np.zeros(X.shape[0]), slots=1, max_params=batch.max_params)
+        engine.upload_programs(batch)
+        K = engine.build_K(batch, batch.pack_theta([np.array(th)], [0.0]))[0]
+        ref = ok.K(ok.parse(name), th, X)
+        assert np.all(np.isfinite(K)), name
+        # the angle-difference identity of PER costs ~1e-16 * |pi x / p| absolute in sin; everything else is ulp-level
+        assert np.allclose(K, ref, rtol=1e-9 if 'PER' in name else 1e-12, atol=1e-290), (name, th, np.max(np.abs(K - ref)))
+
+
 def test_subset_ids_and_quirks(engine):
     from ms_project_b200.program import ProgramBatch
     from oracle import gp
