@@ -43,6 +43,8 @@ struct b200gp_ctx {
   size_t h_cap = 0;
   cudaEvent_t ev[8]{};
   cudaStream_t side = nullptr;     // high-priority stream for the look-ahead panel of large single factorisations
+  cudaStream_t peer = nullptr;     // second stream of the two-group batched schedule
+  bool split_groups = true;
   cudaEvent_t evP = nullptr, evR = nullptr, evS = nullptr;
   float phase_ms[6]{};
   int n_phase = 0;
@@ -131,6 +133,7 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
   cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi);
+  cudaStreamCreateWithFlags(&c->peer, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&c->evP, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->evR, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->evS, cudaEventDisableTiming);
@@ -143,6 +146,7 @@ int b200gp_destroy(b200gp_ctx* c) {
   cudaSetDevice(c->device);
   for (auto& e : c->ev) cudaEventDestroy(e);
   if (c->side) cudaStreamDestroy(c->side);
+  if (c->peer) cudaStreamDestroy(c->peer);
   if (c->evP) { cudaEventDestroy(c->evP); cudaEventDestroy(c->evR); cudaEventDestroy(c->evS); }
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->h_ids) cudaFreeHost(c->h_ids);
@@ -156,7 +160,8 @@ const char* b200gp_last_error(b200gp_ctx* c) { return c ? c->err.c_str() : "null
 
 int b200gp_set_quirks(b200gp_ctx* c, int mask) {
   if (!c) return -1;
-  c->quirks = mask;
+  c->quirks = mask & 255;
+  c->split_groups = !(mask & 512);     // development switch: bit 9 disables the two-group batched schedule
   return 0;
 }
 
@@ -231,9 +236,11 @@ int b200gp_bind(b200gp_ctx* c, void* ws, size_t ws_bytes, int slots, int max_par
 }  // extern "C"
 
 // Panelled right-looking schedule shared by the Cholesky and the L^-T phases.
-//   panel(k0, k1, stream)      finishes tile columns [k0, k1) given every contribution from the left of k0
-//   update(k0, W, j0, j1, st)  applies panel [k0, k0+W) to the columns [j0, j1) to its right, K = 128 W
-//  * many slots: everything on the context stream -- the batch itself fills the GPU;
+//   panel(g, k0, k1, stream)      finishes tile columns [k0, k1) of slot group g given every contribution from the left
+//   update(g, k0, W, j0, j1, st)  applies panel [k0, k0+W) to the columns [j0, j1) to its right, K = 128 W
+//  * many slots: the chunk is split into two slot groups that run the same schedule on two streams, so the
+//    latency-bound steps of one group (in-register diagonal factorisations, K = 128 triangular solves) overlap the
+//    DMMA trailing updates of the other;
 //  * few slots (a single large matrix): look-ahead.  The next panel (its priority update, the latency-bound diagonal
 //    factorisations and the TRSMs) runs on a high-priority side stream while the main stream is still applying the
 //    current panel to the rest of the trailing matrix, so the panel disappears behind the DMMA update.
@@ -241,25 +248,55 @@ template <typename PanelFn, typename UpdateFn>
 static void panel_schedule(b200gp_ctx* c, const Batch& b, PanelFn panel, UpdateFn update) {
   const int T = b.T;
   const bool la = (b.nslots < 8 && T >= 8);
-  cudaStream_t s0 = c->stream, s1 = la ? c->side : c->stream;
-  const int W = la ? c->panel_tiles : c->batch_panel_tiles;
-  if (la) { cudaEventRecord(c->evS, s0); cudaStreamWaitEvent(s1, c->evS, 0); }
-  panel(0, W < T ? W : T, s1);
-  if (la) cudaEventRecord(c->evP, s1);
+  if (!la) {
+    const int W = c->batch_panel_tiles;
+    const bool split = c->split_groups && b.nslots >= 16;
+    Batch g[2] = {b, b};
+    cudaStream_t st[2] = {c->stream, c->stream};
+    int ng = 1;
+    if (split) {
+      ng = 2;
+      g[0].nslots = b.nslots / 2;
+      g[1].slot0 = b.slot0 + g[0].nslots;
+      g[1].nslots = b.nslots - g[0].nslots;
+      st[1] = c->peer;
+      cudaEventRecord(c->evS, c->stream);
+      cudaStreamWaitEvent(c->peer, c->evS, 0);
+    }
+    for (int q = 0; q < ng; q++) {
+      panel(g[q], 0, W < T ? W : T, st[q]);
+      for (int k0 = 0; k0 + W < T; k0 += W) {
+        const int k1 = k0 + W;
+        update(g[q], k0, W, k1, T, st[q]);
+        panel(g[q], k1, (k1 + W < T) ? k1 + W : T, st[q]);
+      }
+    }
+    if (split) {
+      cudaEventRecord(c->evP, c->peer);
+      cudaStreamWaitEvent(c->stream, c->evP, 0);
+    }
+    return;
+  }
+  cudaStream_t s0 = c->stream, s1 = c->side;
+  const int W = c->panel_tiles;
+  cudaEventRecord(c->evS, s0);
+  cudaStreamWaitEvent(s1, c->evS, 0);
+  panel(b, 0, W < T ? W : T, s1);
+  cudaEventRecord(c->evP, s1);
   bool have_r = false;
   for (int k0 = 0; k0 + W < T; k0 += W) {
     const int k1 = k0 + W;
     const int n1 = (k1 + W < T) ? k1 + W : T;                 // end of the next panel
-    if (la) cudaStreamWaitEvent(s0, c->evP, 0);               // panel [k0, k1) is finished
-    if (la && have_r) cudaStreamWaitEvent(s1, c->evR, 0);     // columns [k1, n1) have every earlier trailing update
-    update(k0, W, k1, n1, s1);                                // look-ahead: the next panel's columns first ...
-    if (n1 < T) update(k0, W, n1, T, s0);                     // ... the rest of the trailing matrix meanwhile
-    if (la) cudaEventRecord(c->evR, s0);
+    cudaStreamWaitEvent(s0, c->evP, 0);                       // panel [k0, k1) is finished
+    if (have_r) cudaStreamWaitEvent(s1, c->evR, 0);           // columns [k1, n1) have every earlier trailing update
+    update(b, k0, W, k1, n1, s1);                             // look-ahead: the next panel's columns first ...
+    if (n1 < T) update(b, k0, W, n1, T, s0);                  // ... the rest of the trailing matrix meanwhile
+    cudaEventRecord(c->evR, s0);
     have_r = true;
-    panel(k1, n1, s1);
-    if (la) cudaEventRecord(c->evP, s1);
+    panel(b, k1, n1, s1);
+    cudaEventRecord(c->evP, s1);
   }
-  if (la) cudaStreamWaitEvent(s0, c->evP, 0);
+  cudaStreamWaitEvent(s0, c->evP, 0);
 }
 
 // Right-looking blocked Cholesky of every slot of `b` (M1 in place).
@@ -267,14 +304,14 @@ static void cholesky_phase(b200gp_ctx* c, const Batch& b) {
   const int T = b.T;
   panel_schedule(
       c, b,
-      [&](int k0, int k1, cudaStream_t s) {
-        for (int k = k0; k < k1; k++) {
-          launch_potrf_diag(b, k, s);
-          if (k + 1 < T) launch_gemm(b, GM_TRSM, k, s);
-          if (k + 1 < k1) launch_update(b, UpdRange{k, 1, k + 1, k1}, s);
+      [&](const Batch& g, int k0, int k1, cudaStream_t s) {
+        for (int k = k0; k < k1; k++) {      // left-looking inside the panel: one K = 128 (k - k0) update per column
+          if (k > k0) launch_update(g, UpdRange{k0, k - k0, k, k + 1}, s);
+          launch_potrf_diag(g, k, s);
+          if (k + 1 < T) launch_gemm(g, GM_TRSM, k, s);
         }
       },
-      [&](int k0, int W, int j0, int j1, cudaStream_t s) { launch_update(b, UpdRange{k0, W, j0, j1}, s); });
+      [&](const Batch& g, int k0, int W, int j0, int j1, cudaStream_t s) { launch_update(g, UpdRange{k0, W, j0, j1}, s); });
 }
 
 // Right-looking V = L^-T (upper tiles of M2): column i is finished by V_ji = -S_ji D_i^T (j < i), then pushes its
@@ -282,13 +319,13 @@ static void cholesky_phase(b200gp_ctx* c, const Batch& b) {
 static void inverse_phase(b200gp_ctx* c, const Batch& b) {
   panel_schedule(
       c, b,
-      [&](int k0, int k1, cudaStream_t s) {
-        for (int i = k0; i < k1; i++) {
-          if (i > 0) launch_gemm(b, GM_VTRSM, i, s);
-          if (i + 1 < k1) launch_vupdate(b, UpdRange{i, 1, i + 1, k1}, s);
+      [&](const Batch& g, int k0, int k1, cudaStream_t s) {
+        for (int i = k0; i < k1; i++) {      // left-looking inside the panel, like the Cholesky
+          if (i > k0) launch_vupdate(g, UpdRange{k0, i - k0, i, i + 1}, s);
+          if (i > 0) launch_gemm(g, GM_VTRSM, i, s);
         }
       },
-      [&](int k0, int W, int j0, int j1, cudaStream_t s) { launch_vupdate(b, UpdRange{k0, W, j0, j1}, s); });
+      [&](const Batch& g, int k0, int W, int j0, int j1, cudaStream_t s) { launch_vupdate(g, UpdRange{k0, W, j0, j1}, s); });
 }
 
 // Enqueue all phases for one chunk.  Phase events are recorded only when profiling is on.

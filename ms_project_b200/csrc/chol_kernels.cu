@@ -23,7 +23,7 @@ constexpr int PD_LDL = NB + 1;
 constexpr int PD_SMEM_BYTES = NB * PD_LDL * 8 + (int)sizeof(TilePotrfSmem) + 64;
 
 __global__ void __launch_bounds__(TP_THREADS, 1) potrf_diag_kernel(Batch b, int k) {
-  const int slot = blockIdx.x;
+  const int slot = b.slot0 + blockIdx.x;
   if (b.slot_status[slot] != 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Lsm = reinterpret_cast<double*>(smem_raw);
@@ -96,7 +96,7 @@ void launch_potrf_diag(const Batch& b, int k, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 __device__ __forceinline__ void gemm_body(const Batch& b, int step, const UpdRange& upd, int bx, int hf) {
-  const int slot = blockIdx.y;
+  const int slot = b.slot0 + blockIdx.y;
   if (b.slot_status[slot] != 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* smem = reinterpret_cast<double*>(smem_raw);

@@ -10,6 +10,7 @@ struct Batch {
   // geometry
   int N, Np, T, D;
   int nslots;
+  int slot0;                 // first slot of this launch group (Cholesky / inverse phases split a chunk over two streams)
   size_t mstride;            // Np * Np
   // per-slot scratch (slot-major)
   double* M1;                // K -> L (lower) -> K^-1 (lower)

@@ -18,8 +18,8 @@ cap upd chol_update_kernel 1
 cap vupd inv_update_kernel 3
 cap kinv kinv_kernel 0
 cap trsm chol_trsm_kernel 2
-cap grad grad_kernel 0
-cap build build_k_kernel 0
+cap grad poly_grad_kernel 0
+cap build poly_build_kernel 0
 cap potrf potrf_diag 3
 python bench.py --steps 5 --warmup 3 > $O/bench_$TAG.json 2> $O/bench_$TAG.err
 tail -c 600 $O/bench_$TAG.json

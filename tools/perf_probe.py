@@ -15,6 +15,7 @@ def main():
     eng = get_engine(0)
     import os
     if os.environ.get('PANEL'): eng.set_panel_tiles(int(os.environ['PANEL']))
+    if os.environ.get('QUIRKS'): eng.set_quirks(int(os.environ['QUIRKS']))
     batch = ProgramBatch(kernels)
     slots = eng.slots_for(n, 1, m, batch.max_params)
     print('slots', slots, 'max_params', batch.max_params, 'tokens', batch.tokens.shape)
