@@ -80,6 +80,18 @@ int b200gp_lml_grad(b200gp_ctx* ctx, const int32_t* d_prog, const int32_t* d_pro
                     const int32_t* d_theta_off, const int32_t* d_ids, int n, int with_grad, double* d_lml,
                     double* d_dlml, int32_t* d_status, int32_t* d_tries);
 
+/* GP.predict for ONE item: posterior mean and marginal variance at the Ns test inputs d_Xs (Ns x D
+ * row-major, same standardisation as the bound X), GPy semantics (Posterior._raw_predict + Gaussian.predictive_values;
+ * callers: ModelSelector.predict, src/autoks/core/model_selection/base.py:231-237; KernelKernelGPModel._predict /
+ * get_f_max, src/autoks/gp_regression_models.py:113-134):
+ *     mean = k(x*, X) K_y^-1 y,   var = clip(k(x*, x*) - k(x*, X) K_y^-1 k(X, x*), 1e-15, inf) [+ noise variance]
+ * d_id points at the item id on the device (ids[0..1) of b200gp_lml_grad), `item` is the same id on the host.  The
+ * factorisation runs through the same pipeline and jitter ladder as b200gp_lml_grad; d_lml[item] / d_status[item]
+ * receive its log marginal likelihood and status (NOT_PD: mean and var are NaN).  Synchronises the stream. */
+int b200gp_posterior(b200gp_ctx* ctx, const int32_t* d_prog, const int32_t* d_prog_off, const double* d_theta,
+                     const int32_t* d_theta_off, const int32_t* d_id, int item, const double* d_Xs, int Ns,
+                     int include_likelihood, double* d_mean, double* d_var, double* d_lml, int32_t* d_status);
+
 /* In-place blocked Cholesky of ONE dense SPD matrix (lower triangle; N a multiple of 128), the
  * `dpotrf` of GPy's jitchol at large N.  d_work needs b200gp_potrf_work_bytes(N) bytes.
  * logdet / status are HOST outputs (status 0 ok, >0 = 1-based index of the first bad pivot). */

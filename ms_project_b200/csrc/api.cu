@@ -19,6 +19,9 @@ void launch_hellinger_precompute(const double* Xsub, int n, int D, const int4* p
 void launch_hellinger_pairs(const double* logdet, const double* G, int S, int n, const int* pair_i, const int* pair_j,
                             int npairs, double tol, double* h, int* hstatus, double* dist, int* status, cudaStream_t st);
 void launch_pack_data(const double* X, const double* y, int N, int D, int Np, double* Xt, double* yp, cudaStream_t s);
+void launch_predict(const Batch& b, int item, const double* Xs, int ns, int include_likelihood, double* scratch, double* mean,
+                    double* var, cudaStream_t s);
+int configure_predict_kernels();
 }
 
 struct b200gp_ctx {
@@ -125,7 +128,7 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -3;
   if (prop.major < 10) return -4;   // sm_100a only: there is no fallback path
-  if (configure_kernels() != 0 || configure_hellinger_kernels() != 0) return -5;
+  if (configure_kernels() != 0 || configure_hellinger_kernels() != 0 || configure_predict_kernels() != 0) return -5;
   b200gp_ctx* c = new b200gp_ctx();
   c->device = device;
   c->stream = static_cast<cudaStream_t>(cuda_stream);
@@ -328,6 +331,10 @@ static void inverse_phase(b200gp_ctx* c, const Batch& b) {
       [&](const Batch& g, int k0, int W, int j0, int j1, cudaStream_t s) { launch_vupdate(g, UpdRange{k0, W, j0, j1}, s); });
 }
 
+static int lml_grad_impl(b200gp_ctx* c, const int32_t* prog, const int32_t* prog_off, const double* theta,
+                         const int32_t* theta_off, const int32_t* ids, int n, int with_grad, double* lml, double* dlml,
+                         int32_t* status, int32_t* tries);
+
 // Enqueue all phases for one chunk.  Phase events are recorded only when profiling is on.
 static void run_pipeline(b200gp_ctx* c, const Batch& b, int with_grad) {
   cudaStream_t s = c->stream;
@@ -388,6 +395,16 @@ int b200gp_lml_grad(b200gp_ctx* c, const int32_t* prog, const int32_t* prog_off,
   if (!c->bound) return fail(c, "b200gp_lml_grad: call b200gp_bind first");
   if (!prog || !prog_off || !theta || !theta_off || !ids || !lml || !status || (with_grad && !dlml))
     return fail(c, "b200gp_lml_grad: null pointer");
+  return lml_grad_impl(c, prog, prog_off, theta, theta_off, ids, n, with_grad, lml, dlml, status, tries);
+}
+
+}  // extern "C"
+
+// Scoring pipeline + GPy's jitchol ladder for the items ids[0..n), chunked by the bound slot count.  On return the
+// stream is synchronised and c->h_status[slot] holds the slot status of the last pipeline run of the last chunk.
+static int lml_grad_impl(b200gp_ctx* c, const int32_t* prog, const int32_t* prog_off, const double* theta,
+                         const int32_t* theta_off, const int32_t* ids, int n, int with_grad, double* lml, double* dlml,
+                         int32_t* status, int32_t* tries) {
   CUCHECK(c, cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   for (int off = 0; off < n; off += c->slots) {
@@ -452,6 +469,40 @@ int b200gp_lml_grad(b200gp_ctx* c, const int32_t* prog, const int32_t* prog_off,
         if (c->h_status[i] != 0) { item.push_back(it2[i]); dmean.push_back(dm2[i]); }
     }
   }
+  return 0;
+}
+
+extern "C" {
+
+int b200gp_posterior(b200gp_ctx* c, const int32_t* prog, const int32_t* prog_off, const double* theta,
+                     const int32_t* theta_off, const int32_t* d_id, int item, const double* dXs, int Ns,
+                     int include_likelihood, double* mean, double* var, double* lml, int32_t* status) {
+  if (!c) return -1;
+  if (!c->bound) return fail(c, "b200gp_posterior: call b200gp_bind first");
+  if (!prog || !prog_off || !theta || !theta_off || !d_id || !dXs || !mean || !var || !lml || !status)
+    return fail(c, "b200gp_posterior: null pointer");
+  if (Ns <= 0 || item < 0) return fail(c, "b200gp_posterior: need Ns > 0 and item >= 0");
+  // factorise (with the jitter ladder) exactly as GP.parameters_changed does; slot 0 then holds V = L^-T and alpha
+  int rc = lml_grad_impl(c, prog, prog_off, theta, theta_off, d_id, 1, 0, lml, nullptr, status, nullptr);
+  if (rc != 0) return rc;
+  const double nan_v = NAN;
+  if (c->h_status[0] != 0) {        // not PD even with jitter (GPy raises LinAlgError): NaN predictions, status[item] says why
+    std::vector<double> nv((size_t)Ns, nan_v);
+    CUCHECK(c, cudaMemcpyAsync(mean, nv.data(), sizeof(double) * Ns, cudaMemcpyHostToDevice, c->stream));
+    CUCHECK(c, cudaMemcpyAsync(var, nv.data(), sizeof(double) * Ns, cudaMemcpyHostToDevice, c->stream));
+    CUCHECK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  Batch b = c->base;
+  b.nslots = 1;
+  b.prog = reinterpret_cast<const int4*>(prog); b.prog_off = prog_off; b.theta = theta; b.theta_off = theta_off;
+  const int chunk = b.Np < 4096 ? b.Np : 4096;       // K(x*, X) of a chunk lives in M1 of slot 0, scratch in Dinv
+  for (int off = 0; off < Ns; off += chunk) {
+    const int ns = Ns - off < chunk ? Ns - off : chunk;
+    launch_predict(b, item, dXs + (size_t)off * b.D, ns, include_likelihood, b.Dinv, mean + off, var + off, c->stream);
+  }
+  CUCHECK(c, cudaGetLastError());
+  CUCHECK(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
 

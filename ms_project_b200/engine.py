@@ -180,6 +180,25 @@ class Engine(object):
                                       batch.d_int[:n].data_ptr(), batch.d_int[n:].data_ptr())
         _lib.check(self.ctx, rc, 'b200gp_lml_grad')
 
+    def posterior(self, batch, theta, item, Xs, include_likelihood=True):
+        """GP.predict of item `item` of an uploaded batch at the flat host `theta`: (mean[Ns], var[Ns], lml, status)."""
+        torch = self.torch
+        Xs = np.ascontiguousarray(np.asarray(Xs, dtype=np.float64))
+        if Xs.ndim != 2 or Xs.shape[1] != self.D:
+            raise ValueError('Xnew must be Ns x %d' % self.D)
+        ns = Xs.shape[0]
+        batch.h_theta.numpy()[:] = theta
+        batch.d_theta.copy_(batch.h_theta, non_blocking=True)
+        d_Xs = torch.from_numpy(Xs).to(self.device)
+        d_out = torch.empty(2 * ns, dtype=torch.float64, device=self.device)
+        rc = self.lib.b200gp_posterior(self.ctx, batch.d_tokens.data_ptr(), batch.d_prog_off.data_ptr(), batch.d_theta.data_ptr(),
+                                       batch.d_theta_off.data_ptr(), batch.d_all_ids[item:].data_ptr(), int(item), d_Xs.data_ptr(),
+                                       ns, int(bool(include_likelihood)), d_out[:ns].data_ptr(), d_out[ns:].data_ptr(),
+                                       batch.d_lml.data_ptr(), batch.d_status.data_ptr())
+        _lib.check(self.ctx, rc, 'b200gp_posterior')
+        out = d_out.cpu().numpy()
+        return out[:ns].copy(), out[ns:].copy(), float(batch.d_lml[item].item()), int(batch.d_status[item].item())
+
     def build_K(self, batch, theta, ids=None, add_diag=False):
         """Dense kernel matrices (n x N x N, host numpy) of the selected items over the bound X."""
         torch = self.torch

@@ -14,15 +14,21 @@ class GP(Parameterized):
     def __init__(self, X, Y, kernel, likelihood=None, mean_function=None, inference_method=None, name='gp',
                  Y_metadata=None, normalizer=False, device=0):
         super(GP, self).__init__(name)
-        if mean_function is not None or normalizer:
-            raise NotImplementedError('mean functions / normalisers are outside the scoring path')
+        if mean_function is not None:
+            raise NotImplementedError('mean functions are outside the scoring path')
         X = np.asarray(X, dtype=np.float64)
         Y = np.asarray(Y, dtype=np.float64)
         assert X.ndim == 2, 'X must be N x D'
         if Y.ndim == 1:
             Y = Y[:, None]
         assert Y.shape == (X.shape[0], 1), 'the scoring path is single-output GP regression (Y is N x 1)'
-        self.X, self.Y = X, Y
+        # GPy's `normalizer=True` (GPRegression(..., normalizer=True) in KernelKernelGPModel._create_model,
+        # src/autoks/gp_regression_models.py:79-80) is the Standardize normaliser: the GP sees (Y - mean) / std and
+        # predictions are mapped back (mean * std + mean, var * std^2)
+        self.normalizer = bool(normalizer)
+        self.Y_raw = Y
+        self._set_Y(Y)
+        self.X = X
         self.num_data, self.input_dim = X.shape
         self.kern = kernel
         self.likelihood = Gaussian() if likelihood is None else likelihood
@@ -34,6 +40,14 @@ class GP(Parameterized):
         self._device = device
         self._lml = None
         self._status = 0
+
+    def _set_Y(self, Y):
+        if self.normalizer:
+            self._y_mean, self._y_std = float(Y.mean()), float(Y.std())
+            self.Y = (Y - self._y_mean) / self._y_std
+        else:
+            self._y_mean, self._y_std = 0.0, 1.0
+            self.Y = Y
 
     # ------------------------------------------------------------------ device evaluation
     def _engine(self):
@@ -107,8 +121,29 @@ class GP(Parameterized):
             self.X = np.asarray(X, dtype=np.float64)
             self.num_data = self.X.shape[0]
         if Y is not None:
-            self.Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)
+            self.Y_raw = np.asarray(Y, dtype=np.float64).reshape(-1, 1)
+            self._set_Y(self.Y_raw)
         self._lml = None
 
     def predict(self, Xnew, full_cov=False, Y_metadata=None, kern=None, likelihood=None, include_likelihood=True):
-        raise NotImplementedError('posterior prediction is the next row after the scoring path (SURVEY.md 8f, f4)')
+        """GP.predict: posterior mean and marginal variance at Xnew, each Ns x 1 (GPy Posterior._raw_predict +
+        Gaussian.predictive_values; callers: base.py:231-237, gp_regression_models.py:113-134), through
+        b200gp_posterior.  NOT_PD even after the jitter ladder raises LinAlgError like GPy."""
+        if full_cov:
+            raise NotImplementedError('full_cov=True is not used by the reference path and is not implemented')
+        if kern is not None or likelihood is not None:
+            raise NotImplementedError('predict with a replacement kernel / likelihood is not implemented')
+        from ..program import ProgramBatch
+        Xnew = np.asarray(Xnew, dtype=np.float64)
+        if Xnew.ndim == 1:
+            Xnew = Xnew[None, :]
+        eng = self._engine()
+        batch = ProgramBatch([self.kern])
+        eng.ensure_bound(self.X, self.Y, 1, batch.max_params)
+        eng.upload_programs(batch)
+        theta = batch.pack_theta([self.kern.param_array], [float(self.likelihood.variance)])
+        mean, var, lml, status = eng.posterior(batch, theta, 0, Xnew, include_likelihood=include_likelihood)
+        self._lml, self._status = lml, status
+        if status == 2:
+            raise np.linalg.LinAlgError('not positive definite, even with jitter.')
+        return (mean * self._y_std + self._y_mean)[:, None], (var * self._y_std ** 2)[:, None]
