@@ -38,7 +38,8 @@ extern "C" {
 typedef struct b200gp_ctx b200gp_ctx;
 
 enum { B200GP_OP_SE = 0, B200GP_OP_RQ = 1, B200GP_OP_PER = 2, B200GP_OP_LIN = 3, B200GP_OP_CONST = 4,
-       B200GP_OP_ADD = 5, B200GP_OP_MUL = 6 };
+       B200GP_OP_ADD = 5, B200GP_OP_MUL = 6,
+       B200GP_OP_LOOKUP = 7 /* {op, index_dim, theta_offset}: RBF over a looked-up distance, see b200gp_set_lookup */ };
 
 /* per-item status */
 enum { B200GP_OK = 0, B200GP_JITTERED = 1, B200GP_NOT_PD = 2, B200GP_NONFINITE = 3 };
@@ -55,6 +56,13 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out);
 int b200gp_destroy(b200gp_ctx* ctx);
 const char* b200gp_last_error(b200gp_ctx* ctx);
 int b200gp_set_quirks(b200gp_ctx* ctx, int quirk_mask);
+
+/* Distance table of the OP_LOOKUP leaf: the BOMS surrogate's RBFDistanceBuilderKernelKernel
+ * (src/autoks/core/strategies/bayes_opt_gp_strategy.py:27-28; kernel-kernel.ipynb#2) evaluates
+ * k(i, j) = variance * exp(-1/2 (D[i][j] / lengthscale)^2) over model indices stored in X.  d_table is n x n row-major
+ * (DistanceBuilder.get_kernel(n)); indices outside [0, n) or NaN entries give NaN.  (NULL, 0) clears it.  The pointer is
+ * borrowed: it must stay valid while programs with OP_LOOKUP leaves are evaluated. */
+int b200gp_set_lookup(b200gp_ctx* ctx, const double* d_table, int n);
 
 /* Workspace needed to score `slots` matrices of order N at a time (bytes). */
 size_t b200gp_workspace_bytes(int N, int D, int slots, int max_params);

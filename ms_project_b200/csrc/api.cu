@@ -48,6 +48,8 @@ struct b200gp_ctx {
   cudaStream_t side = nullptr;     // high-priority stream for the look-ahead panel of large single factorisations
   cudaStream_t peer = nullptr;     // second stream of the two-group batched schedule
   bool split_groups = true;
+  const double* lut = nullptr;     // OP_LOOKUP table (b200gp_set_lookup)
+  int lut_n = 0;
   cudaEvent_t evP = nullptr, evR = nullptr, evS = nullptr;
   float phase_ms[6]{};
   int n_phase = 0;
@@ -165,6 +167,14 @@ int b200gp_set_quirks(b200gp_ctx* c, int mask) {
   if (!c) return -1;
   c->quirks = mask & 255;
   c->split_groups = !(mask & 512);     // development switch: bit 9 disables the two-group batched schedule
+  return 0;
+}
+
+int b200gp_set_lookup(b200gp_ctx* c, const double* d_table, int n) {
+  if (!c) return -1;
+  if ((d_table == nullptr) != (n == 0) || n < 0) return fail(c, "b200gp_set_lookup: need (table, n > 0) or (NULL, 0)");
+  c->lut = d_table;
+  c->lut_n = n;
   return 0;
 }
 
@@ -378,7 +388,7 @@ int b200gp_build_K(b200gp_ctx* c, const int32_t* prog, const int32_t* prog_off, 
     b.nslots = (n - off < c->slots) ? n - off : c->slots;
     b.ids = ids + off;
     b.prog = reinterpret_cast<const int4*>(prog); b.prog_off = prog_off; b.theta = theta; b.theta_off = theta_off;
-    b.quirks = c->quirks;
+    b.quirks = c->quirks; b.lut = c->lut; b.lut_n = c->lut_n;
     b.add_diag = add_diag;
     launch_compile(b, c->stream);
     launch_build_k(b, c->stream);
@@ -414,7 +424,7 @@ static int lml_grad_impl(b200gp_ctx* c, const int32_t* prog, const int32_t* prog
     b.prog = reinterpret_cast<const int4*>(prog); b.prog_off = prog_off; b.theta = theta; b.theta_off = theta_off;
     b.lml = lml; b.dlml = dlml; b.status = status; b.tries = tries; b.try_no = 0;
     b.jitter = nullptr;
-    b.quirks = c->quirks;
+    b.quirks = c->quirks; b.lut = c->lut; b.lut_n = c->lut_n;
     b.add_diag = 1;
     run_pipeline(c, b, with_grad);
     CUCHECK(c, cudaGetLastError());
@@ -496,6 +506,7 @@ int b200gp_posterior(b200gp_ctx* c, const int32_t* prog, const int32_t* prog_off
   Batch b = c->base;
   b.nslots = 1;
   b.prog = reinterpret_cast<const int4*>(prog); b.prog_off = prog_off; b.theta = theta; b.theta_off = theta_off;
+  b.lut = c->lut; b.lut_n = c->lut_n;
   const int chunk = b.Np < 4096 ? b.Np : 4096;       // K(x*, X) of a chunk lives in M1 of slot 0, scratch in Dinv
   for (int off = 0; off < Ns; off += chunk) {
     const int ns = Ns - off < chunk ? Ns - off : chunk;

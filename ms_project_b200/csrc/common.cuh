@@ -16,7 +16,10 @@ constexpr int MAX_STACK = 8;       // evaluation-stack depth
 // ---- kernel-program opcodes (host compiles Covariance.postfix_tokens into these) ---------------
 // token = int4 {op, a, b, c}: leaf  -> {op, active_dim, theta_offset, 0}
 //                             ADD/MUL -> {op, lhs_token, rhs_token, 0}
-enum Op : int { OP_SE = 0, OP_RQ = 1, OP_PER = 2, OP_LIN = 3, OP_CONST = 4, OP_ADD = 5, OP_MUL = 6 };
+//                             LOOKUP -> {op, index_dim, theta_offset, 0}: RBF over a looked-up distance matrix
+//                                       (RBFDistanceBuilderKernelKernel of the BOMS surrogate; the inputs are model indices)
+enum Op : int { OP_SE = 0, OP_RQ = 1, OP_PER = 2, OP_LIN = 3, OP_CONST = 4, OP_ADD = 5, OP_MUL = 6, OP_LOOKUP = 7 };
+__host__ __device__ inline bool is_leaf(int op) { return op <= OP_CONST || op == OP_LOOKUP; }
 
 // gradient quirk bits (SURVEY.md 8c hazard 3): reproduce the notebook formulas of the fork
 constexpr int QUIRK_PER_LENGTHSCALE = 1;   // dK/dl of PER 4x too small (periodic.ipynb#2)

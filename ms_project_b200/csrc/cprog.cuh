@@ -28,7 +28,7 @@ struct __align__(16) CProg {
 static_assert(sizeof(CProg) == 176, "CProg layout");
 
 __host__ __device__ inline int leaf_param_count(int op) {
-  return (op == OP_RQ || op == OP_PER) ? 3 : (op == OP_CONST ? 1 : 2);
+  return (op == OP_RQ || op == OP_PER) ? 3 : (op == OP_CONST ? 1 : 2);      // SE, LIN, LOOKUP: 2
 }
 
 }  // namespace b200gp

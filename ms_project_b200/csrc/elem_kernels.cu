@@ -41,6 +41,7 @@ __device__ void compile_one(const Batch& b, int slot) {
     bool ok = true;
     for (int t = 0; t < nt && ok; t++) {
       const int4 k = b.prog[t0 + t];
+      if (k.x == OP_LOOKUP) { ok = false; break; }      // table look-ups stay with the interpreter
       if (k.x <= OP_CONST) {
         if (L >= CP_LMAX) { ok = false; break; }
         cp.leaf[L] = make_int4(k.x, k.y, k.z, leaf_param_count(k.x));
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(256) interp_build_kernel(Batch b) {
     int ti, tj;
     tri_decode((int)(w % ntiles), ti, tj);
     __syncthreads();
-    load_program(S.P, b.prog, b.prog_off, b.theta, b.theta_off, item);
+    load_program(S.P, b.prog, b.prog_off, b.theta, b.theta_off, item, b.lut, b.lut_n);
     stage_inputs(S, b, ti, tj);
     __syncthreads();
     const double diag_add = b.add_diag ? S.P.noise + EXACT_INFERENCE_JITTER + (b.jitter ? b.jitter[slot] : 0.0) : 0.0;
@@ -583,7 +584,7 @@ __global__ void __launch_bounds__(256) interp_grad_kernel(Batch b) {
     int ti, tj;
     tri_decode(tile, ti, tj);
     __syncthreads();
-    load_program(S.P, b.prog, b.prog_off, b.theta, b.theta_off, item);
+    load_program(S.P, b.prog, b.prog_off, b.theta, b.theta_off, item, b.lut, b.lut_n);
     stage_inputs(S, b, ti, tj);
     if (threadIdx.x < NB) {
       S.ai[threadIdx.x] = b.alpha[(size_t)slot * b.Np + ti * NB + threadIdx.x];

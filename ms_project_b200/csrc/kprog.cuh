@@ -17,19 +17,30 @@ struct ProgSmem {
   int ntok;
   int nparam;                  // kernel parameters (noise excluded)
   double noise;                // Gaussian_noise.variance
+  const double* lut;           // OP_LOOKUP: lut_n x lut_n distance matrix (b200gp_set_lookup), else null
+  int lut_n;
 };
+
+// distance between the models whose indices are stored (as doubles) in a and b; NaN outside the table
+__device__ __forceinline__ double lookup_distance(const ProgSmem& P, double a, double b) {
+  const int ia = (int)a, ib = (int)b;
+  if (P.lut == nullptr || ia < 0 || ib < 0 || ia >= P.lut_n || ib >= P.lut_n) return nan("");
+  return P.lut[(size_t)ia * P.lut_n + ib];
+}
 
 // Cooperative load of item `item`'s program + theta into shared memory; derives leaf constants.
 // `th_base` points at the item's first kernel parameter; `noise` is its Gaussian noise variance.
 __device__ inline void load_program_at(ProgSmem& P, const int4* __restrict__ toks, int nt,
-                                       const double* __restrict__ th_base, int nparam, double noise) {
+                                       const double* __restrict__ th_base, int nparam, double noise,
+                                       const double* lut = nullptr, int lut_n = 0) {
   for (int t = threadIdx.x; t < nt; t += blockDim.x) {
     int4 k = toks[t];
     P.tok[t] = k;
     double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    if (k.x <= OP_CONST) {
+    if (is_leaf(k.x)) {
       const double* th = th_base + k.z;
       switch (k.x) {
+        case OP_LOOKUP:
         case OP_SE:  c0 = th[0]; c1 = 1.0 / th[1]; break;                                   // [variance, lengthscale]
         case OP_RQ:  c0 = th[0]; c1 = 1.0 / th[1]; c2 = th[2]; c3 = 1.0 / (2.0 * th[2]); break;  // [.., power]
         case OP_PER: c0 = th[0]; c1 = 3.14159265358979323846 / th[1]; c2 = 1.0 / th[2]; c3 = 1.0 / th[1]; break;  // [variance, period, lengthscale]
@@ -38,19 +49,22 @@ __device__ inline void load_program_at(ProgSmem& P, const int4* __restrict__ tok
       }
     }
     P.cst[t][0] = c0; P.cst[t][1] = c1; P.cst[t][2] = c2; P.cst[t][3] = c3;
-    P.ivar[t] = (k.x <= OP_CONST) ? 1.0 / c0 : 0.0;
+    P.ivar[t] = is_leaf(k.x) ? 1.0 / c0 : 0.0;
   }
   if (threadIdx.x == 0) {
     P.ntok = nt;
     P.nparam = nparam;
     P.noise = noise;
+    P.lut = lut;
+    P.lut_n = lut_n;
   }
 }
 
 __device__ inline void load_program(ProgSmem& P, const int4* __restrict__ prog, const int* __restrict__ prog_off,
-                                    const double* __restrict__ theta, const int* __restrict__ theta_off, int item) {
+                                    const double* __restrict__ theta, const int* __restrict__ theta_off, int item,
+                                    const double* lut = nullptr, int lut_n = 0) {
   const int t0 = prog_off[item], th0 = theta_off[item], th1 = theta_off[item + 1];
-  load_program_at(P, prog + t0, prog_off[item + 1] - t0, theta + th0, th1 - th0 - 1, theta[th1 - 1]);
+  load_program_at(P, prog + t0, prog_off[item + 1] - t0, theta + th0, th1 - th0 - 1, theta[th1 - 1], lut, lut_n);
 }
 
 // K(x_i, x_j).  xi / xj point at dimension 0 of the staged inputs; consecutive dimensions are
@@ -61,10 +75,11 @@ static __device__ __noinline__ double eval_K(const ProgSmem& P, const double* xi
   for (int t = 0; t < nt; t++) {
     const int4 k = P.tok[t];
     double v;
-    if (k.x <= OP_CONST) {
+    if (is_leaf(k.x)) {
       const double a = xi[k.y * stride], b = xj[k.y * stride];
       const double c0 = P.cst[t][0], c1 = P.cst[t][1];
       switch (k.x) {
+        case OP_LOOKUP: { double r = lookup_distance(P, a, b) * c1; v = c0 * exp(-0.5 * (r * r)); break; }
         case OP_SE: { double r = (a - b) * c1; v = c0 * exp(-0.5 * (r * r)); break; }
         case OP_RQ: { double r = (a - b) * c1; v = c0 * exp(-P.cst[t][2] * log1p((r * r) * P.cst[t][3])); break; }
         case OP_PER: { double q = sin((a - b) * c1) * P.cst[t][2]; v = c0 * exp(-2.0 * (q * q)); break; }
@@ -89,10 +104,11 @@ static __device__ __noinline__ void eval_grad(const ProgSmem& P, const double* x
   for (int t = 0; t < nt; t++) {
     const int4 k = P.tok[t];
     double v, a0 = 0, a1 = 0;
-    if (k.x <= OP_CONST) {
+    if (is_leaf(k.x)) {
       const double a = xi[k.y * stride], b = xj[k.y * stride];
       const double c0 = P.cst[t][0], c1 = P.cst[t][1];
       switch (k.x) {
+        case OP_LOOKUP: { double r = lookup_distance(P, a, b) * c1; a0 = r * r; a1 = exp(-0.5 * a0); v = c0 * a1; break; }
         case OP_SE: { double r = (a - b) * c1; a0 = r * r; a1 = exp(-0.5 * a0); v = c0 * a1; break; }
         case OP_RQ: { double r = (a - b) * c1; double u = (r * r) * P.cst[t][3]; a0 = log1p(u); a1 = u; v = c0 * exp(-P.cst[t][2] * a0); break; }
         case OP_PER: { double s, c; sincos((a - b) * c1, &s, &c); a0 = s; a1 = c; double q = s * P.cst[t][2]; v = c0 * exp(-2.0 * (q * q)); break; }
@@ -118,6 +134,7 @@ static __device__ __noinline__ void eval_grad(const ProgSmem& P, const double* x
       const double c0 = P.cst[t][0], c1 = P.cst[t][1];
       double* o = acc + k.z;
       switch (k.x) {
+        case OP_LOOKUP: // same Stationary RBF gradients with r = D[i, j] / l   (kernel-kernel.ipynb#2)
         case OP_SE:     // dK/dv = K/v ; dK/dl = K r^2 / l   (stationary.py update_gradients_full)
           o[0] += g * ax1[t];
           o[1] += g * (v * ax0[t] * c1);

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) cross_k_kernel(Batch b, int item, const d
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CrossSmem& S = *reinterpret_cast<CrossSmem*>(smem_raw);
   const int tp = blockIdx.y, tc = blockIdx.x;
-  load_program(S.P, b.prog, b.prog_off, b.theta, b.theta_off, item);
+  load_program(S.P, b.prog, b.prog_off, b.theta, b.theta_off, item, b.lut, b.lut_n);
   for (int idx = threadIdx.x; idx < b.D * NB; idx += blockDim.x) {
     const int d = idx / NB, r = idx % NB;
     const int pt = tp * NB + r;

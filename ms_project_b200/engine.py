@@ -116,6 +116,11 @@ class Engine(object):
             raise ValueError('batch has kernels with %d parameters; engine bound for %d' % (batch.max_params, self.max_params))
         if batch.max_dim >= self.D:
             raise ValueError('a kernel uses input dimension %d but X has %d columns' % (batch.max_dim, self.D))
+        if getattr(batch, 'lookup', None) is not None:      # OP_LOOKUP leaves: (re-)upload the builder's distance table
+            builder, n_models = batch.lookup
+            table = np.ascontiguousarray(np.asarray(builder.get_kernel(n_models), dtype=np.float64))
+            self._lut = torch.from_numpy(table).to(self.device)
+            _lib.check(self.ctx, self.lib.b200gp_set_lookup(self.ctx, self._lut.data_ptr(), int(table.shape[0])), 'b200gp_set_lookup')
         batch.d_tokens = torch.from_numpy(batch.tokens.reshape(-1)).to(self.device)
         batch.d_prog_off = torch.from_numpy(batch.prog_off).to(self.device)
         batch.d_theta_off = torch.from_numpy(batch.theta_off).to(self.device)

@@ -38,6 +38,7 @@ class GP(Parameterized):
         self.link_parameters(self.kern, self.likelihood)
         self.optimization_runs = []
         self._device = device
+        self._role = 'search'          # engine cache key: the BOMS surrogate uses its own so the search's bound data stays
         self._lml = None
         self._status = 0
 
@@ -52,7 +53,7 @@ class GP(Parameterized):
     # ------------------------------------------------------------------ device evaluation
     def _engine(self):
         from ..engine import get_engine
-        return get_engine(self._device)
+        return get_engine(self._device, self._role)
 
     def _evaluate(self, with_grad=True):
         from ..program import ProgramBatch

@@ -127,6 +127,38 @@ class RBF(Stationary):
         return d
 
 
+@_register('GPy.kern.RBFDistanceBuilderKernelKernel')
+class RBFDistanceBuilderKernelKernel(Stationary):
+    """The BOMS "kernel kernel" (fork class used at src/autoks/core/strategies/bayes_opt_gp_strategy.py:27-28; source
+    in notebooks/exploratory/test custom kernels/kernel-kernel.ipynb#2): a Stationary RBF whose unscaled distance
+    between two inputs -- model INDICES -- is looked up in the distance builder's matrix,
+        k(i, j) = variance * exp(-1/2 (D[i, j] / lengthscale)^2),   D = distance_builder.get_kernel(n_models).
+    On the device this is the OP_LOOKUP leaf; the table is uploaded whenever a program batch holding the leaf is."""
+    op_name = 'LOOKUP'
+
+    def __init__(self, distance_builder, n_models, input_dim=1, variance=1., lengthscale=None, ARD=False, active_dims=None,
+                 name='kernel_kernel', useGPU=False):
+        super(RBFDistanceBuilderKernelKernel, self).__init__(input_dim, variance, lengthscale, ARD, active_dims, name,
+                                                             useGPU=useGPU)
+        self.distance_builder = distance_builder
+        self.n_models = int(n_models)
+
+    def __deepcopy__(self, memo):
+        # copies share the builder (it owns device state and the NaN-initialised distance matrix)
+        import copy as _c
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for key, val in self.__dict__.items():
+            new.__dict__[key] = val if key == 'distance_builder' else _c.deepcopy(val, memo)
+        return new
+
+    def to_dict(self):
+        d = super(RBFDistanceBuilderKernelKernel, self)._save_to_input_dict()
+        d['class'] = 'GPy.kern.RBFDistanceBuilderKernelKernel'
+        d['n_models'] = self.n_models
+        return d
+
+
 @_register('GPy.kern.RationalQuadratic')
 class RationalQuadratic(Stationary):
     """k = variance * (1 + r^2 / (2 power))^-power   (rational-quadratic.ipynb#2)."""

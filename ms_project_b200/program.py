@@ -8,7 +8,11 @@ import numpy as np
 
 from .gpy_compat.kern import Kern, Add, Prod, CombinationKernel
 
-OPCODES = {'SE': 0, 'RQ': 1, 'PER': 2, 'LIN': 3, 'CONST': 4, '+': 5, '*': 6}
+OPCODES = {'SE': 0, 'RQ': 1, 'PER': 2, 'LIN': 3, 'CONST': 4, '+': 5, '*': 6, 'LOOKUP': 7}
+
+
+def _leaf_rows(t):
+    return (t[:, 0] <= 4) | (t[:, 0] == 7)
 MAX_TOKENS = 64
 MAX_PARAMS = 128
 MAX_STACK = 8
@@ -125,7 +129,17 @@ class ProgramBatch(object):
         self.theta_off = np.zeros(self.n_items + 1, dtype=np.int32)
         self.theta_off[1:] = np.cumsum(self.n_params + 1)
         self.max_params = int(self.n_params.max()) if self.n_items else 1
-        self.max_dim = int(max((t[t[:, 0] <= 4, 1].max() for t, _ in progs), default=0))
+        self.max_dim = int(max((t[_leaf_rows(t), 1].max() for t, _ in progs), default=0))
+        # OP_LOOKUP leaves (BOMS surrogate): every such leaf of a batch reads ONE distance table, the builder's
+        self.lookup = None
+        for k in self.kernels:
+            k.traverse(self._note_lookup)
+
+    def _note_lookup(self, k):
+        if getattr(k, 'op_name', None) == 'LOOKUP':
+            if self.lookup is not None and self.lookup[0] is not k.distance_builder:
+                raise ValueError('all table look-up leaves of one batch must share the distance builder')
+            self.lookup = (k.distance_builder, max(int(k.n_models), self.lookup[1] if self.lookup else 0))
 
     def pack_theta(self, kernel_thetas, noise_vars):
         """Flat theta in device layout: per item [kernel params..., noise variance]."""

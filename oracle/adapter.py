@@ -2,7 +2,8 @@
 `.active_dims`, and the family read from the class name) -> oracle expression tree.  TEST INFRASTRUCTURE.
 It imports nothing from the product package."""
 
-_FAMILY = {'RBF': 'SE', 'RationalQuadratic': 'RQ', 'StandardPeriodic': 'PER', 'LinScaleShift': 'LIN', 'Bias': 'CONST'}
+_FAMILY = {'RBF': 'SE', 'RationalQuadratic': 'RQ', 'StandardPeriodic': 'PER', 'LinScaleShift': 'LIN', 'Bias': 'CONST',
+           'RBFDistanceBuilderKernelKernel': 'KK'}
 
 
 def to_oracle_expr(kernel):

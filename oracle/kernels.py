@@ -25,17 +25,34 @@ from functools import reduce
 
 import numpy as np
 
-N_PARAMS = {'SE': 2, 'RQ': 3, 'PER': 3, 'LIN': 2, 'CONST': 1}
+N_PARAMS = {'SE': 2, 'RQ': 3, 'PER': 3, 'LIN': 2, 'CONST': 1, 'KK': 2}
 PARAM_NAMES = {
     'SE': ['variance', 'lengthscale'],
     'RQ': ['variance', 'lengthscale', 'power'],
     'PER': ['variance', 'period', 'lengthscale'],
     'LIN': ['variances', 'shifts'],
     'CONST': ['variance'],
+    'KK': ['variance', 'lengthscale'],
 }
 # GPy constructor defaults (all 1.0, RQ power 2.0): rational-quadratic.ipynb#2 `power=2.`,
 # periodic.ipynb#2 / linear.ipynb#2 `np.ones(1)`.
-DEFAULTS = {'SE': [1., 1.], 'RQ': [1., 1., 2.], 'PER': [1., 1., 1.], 'LIN': [1., 1.], 'CONST': [1.]}
+DEFAULTS = {'SE': [1., 1.], 'RQ': [1., 1., 2.], 'PER': [1., 1., 1.], 'LIN': [1., 1.], 'CONST': [1.], 'KK': [1., 1.]}
+
+# 'KK': the BOMS "kernel kernel" (notebooks/exploratory/test custom kernels/kernel-kernel.ipynb#2; fork class
+# RBFDistanceBuilderKernelKernel, src/autoks/core/strategies/bayes_opt_gp_strategy.py:27-28): a Stationary RBF whose
+# unscaled distance between two inputs (model indices) is looked up in a distance matrix.  The table is oracle-global.
+LOOKUP_TABLE = [None]
+
+
+def set_lookup_table(D):
+    LOOKUP_TABLE[0] = None if D is None else np.asarray(D, dtype=np.float64)
+
+
+def _lookup_dist(x, x2):
+    D = LOOKUP_TABLE[0]
+    i = np.asarray(x).astype(int)
+    j = i if x2 is None else np.asarray(x2).astype(int)
+    return D[np.ix_(i, j)]
 
 
 # ----------------------------------------------------------------------------- expression utils
@@ -168,6 +185,10 @@ def _leaf_K(fam, th, x, x2, mode):
         v, c = th
         xx2 = x if x2 is None else x2
         return np.outer(x - c, xx2 - c) * v                   # linear.ipynb#2 K (non-ARD)
+    if fam == 'KK':
+        v, l = th
+        r = _lookup_dist(x, x2) / l                           # kernel-kernel.ipynb#2 _scaled_dist
+        return v * np.exp(-0.5 * r ** 2)                      # K_of_r
     if fam == 'CONST':
         n2 = x.shape[0] if x2 is None else x2.shape[0]
         return np.full((x.shape[0], n2), th[0], dtype=np.float64)   # GPy Bias.K
@@ -192,6 +213,11 @@ def _leaf_grad(fam, th, x, dL_dK, mode, quirks):
         r2 = np.square(r) + np.spacing(1)
         dK_dpow = K * (np.exp(np.log(r2) - np.log(r2 + 2. * a)) - np.log1p(r2 / (2. * a)))
         return [g_v, g_l, np.sum(dL_dK * dK_dpow)]
+    if fam == 'KK':                                           # Stationary.update_gradients_full with the looked-up r
+        v, l = th
+        r = _lookup_dist(x, None) / l
+        K = _leaf_K(fam, th, x, None, mode)
+        return [np.sum(K * dL_dK) / v, -np.sum(-r * K * dL_dK * r) / l]
     if fam == 'PER':
         v, p, l = th
         base = np.pi * (x[:, None] - x[None, :]) / p
