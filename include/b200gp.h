@@ -124,6 +124,13 @@ int b200gp_hellinger_pairs(b200gp_ctx* ctx, const double* d_logdet, const double
                            const int32_t* d_pair_i, const int32_t* d_pair_j, int npairs, double tol_logdet, void* d_work,
                            double* d_dist, int32_t* d_status);
 
+/* Frobenius (metric 0) / correlation (metric 1) distance between the sampled prior Gram matrices of model pairs
+ * (FrobeniusDistanceBuilder.frobenius_distance / CorrelationDistanceBuilder.correlation_distance,
+ * src/autoks/distance/distance.py:208-212,242-265).  d_G is the [M][S][n][n] stack b200gp_hellinger_precompute wrote
+ * (the reference's vec(K_s + lambda_s I) columns, which it stores in float32: entries are rounded to float32 here too). */
+int b200gp_vector_pairs(b200gp_ctx* ctx, const double* d_G, int M, int S, int n, const int32_t* d_pair_i,
+                        const int32_t* d_pair_j, int npairs, int metric, double* d_dist);
+
 /* Phase timings (ms) of the most recent b200gp_lml_grad chunk, measured with CUDA events on the context
  * stream: [build_K, cholesky, inverse(V), solve, Kinv, grad+finalize].  Returns the number written. */
 int b200gp_last_phase_ms(b200gp_ctx* ctx, float* out, int cap);

@@ -18,6 +18,8 @@ void launch_hellinger_precompute(const double* Xsub, int n, int D, const int4* p
                                  double* logdet, double* G, int* status, cudaStream_t st);
 void launch_hellinger_pairs(const double* logdet, const double* G, int S, int n, const int* pair_i, const int* pair_j,
                             int npairs, double tol, double* h, int* hstatus, double* dist, int* status, cudaStream_t st);
+void launch_vector_pairs(const double* G, int S, int n, const int* pair_i, const int* pair_j, int npairs, int metric,
+                         double* dist, cudaStream_t st);
 void launch_pack_data(const double* X, const double* y, int N, int D, int Np, double* Xt, double* yp, cudaStream_t s);
 void launch_predict(const Batch& b, int item, const double* Xs, int ns, int include_likelihood, double* scratch, double* mean,
                     double* var, cudaStream_t s);
@@ -593,6 +595,18 @@ int b200gp_hellinger_pairs(b200gp_ctx* c, const double* logdet, const double* G,
   double* h = cv.take<double>((size_t)npairs * S);
   int* hs = cv.take<int>((size_t)npairs * S);
   launch_hellinger_pairs(logdet, G, S, n, pair_i, pair_j, npairs, tol_logdet, h, hs, dist, status, c->stream);
+  CUCHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int b200gp_vector_pairs(b200gp_ctx* c, const double* G, int M, int S, int n, const int32_t* pair_i, const int32_t* pair_j,
+                        int npairs, int metric, double* dist) {
+  if (!c) return -1;
+  if (!G || !pair_i || !pair_j || !dist) return fail(c, "b200gp_vector_pairs: null pointer");
+  if (n <= 0 || M <= 0 || S <= 0 || (metric != 0 && metric != 1)) return fail(c, "b200gp_vector_pairs: bad geometry / metric");
+  if (npairs <= 0) return 0;
+  CUCHECK(c, cudaSetDevice(c->device));
+  launch_vector_pairs(G, S, n, pair_i, pair_j, npairs, metric, dist, c->stream);
   CUCHECK(c, cudaGetLastError());
   return 0;
 }

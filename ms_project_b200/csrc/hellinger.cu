@@ -128,6 +128,72 @@ __global__ void hellinger_reduce_kernel(const double* __restrict__ h, const int*
   status[pr] = bad;
 }
 
+// Frobenius / correlation distance between the vec(K_s + lambda_s I) samples of two models
+// (FrobeniusDistanceBuilder / CorrelationDistanceBuilder, src/autoks/distance/distance.py:197-284).  The reference keeps
+// the vectors in float32, so every entry is rounded to float32 first; the sums themselves run in FP64 (the reference's
+// float32 accumulations are the larger error).  One CTA per pair, all S samples, fixed reduction order.
+//   metric 0:  mean_s sqrt(sum_k (a_ks - b_ks)^2)
+//   metric 1:  mean_s sqrt(1/2 (1 - clip(corr(a_s, b_s), 0, 1)))
+__global__ void __launch_bounds__(256) vector_pair_kernel(const double* __restrict__ G, int S, int n, const int* __restrict__ pair_i,
+                                                          const int* __restrict__ pair_j, int metric, double* __restrict__ dist) {
+  __shared__ double red[8][5];
+  __shared__ double acc_s;
+  const int pr = blockIdx.x;
+  const int mi = pair_i[pr], mj = pair_j[pr];
+  const int n2 = n * n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) acc_s = 0.0;
+  for (int s = 0; s < S; s++) {
+    const double* a = G + ((size_t)mi * S + s) * n2;
+    const double* b = G + ((size_t)mj * S + s) * n2;
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};      // sum a, sum b, sum ab, sum aa, sum bb  |  v[0] = sum (a-b)^2
+    for (int k = threadIdx.x; k < n2; k += blockDim.x) {
+      const double x = (double)(float)a[k], y = (double)(float)b[k];
+      if (metric == 0) {
+        const double d = (double)((float)x - (float)y);      // the float32 difference the reference squares
+        v[0] = fma(d, d, v[0]);
+      } else {
+        v[0] += x; v[1] += y;
+        v[2] = fma(x, y, v[2]); v[3] = fma(x, x, v[3]); v[4] = fma(y, y, v[4]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+      double t = v[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) red[warp][q] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t[5];
+      for (int q = 0; q < 5; q++) {
+        t[q] = 0.0;
+        for (int w = 0; w < 8; w++) t[q] += red[w][q];
+      }
+      double d;
+      if (metric == 0) {
+        d = sqrt(t[0]);
+      } else {
+        const double inv = 1.0 / n2;
+        const double cab = t[2] - t[0] * t[1] * inv, caa = t[3] - t[0] * t[0] * inv, cbb = t[4] - t[1] * t[1] * inv;
+        double corr = cab / (sqrt(caa) * sqrt(cbb));
+        corr = fmin(fmax(corr, 0.0), 1.0);       // NaN (a constant vector) stays NaN like np.clip
+        d = sqrt(0.5 * (1.0 - corr));
+      }
+      acc_s += d;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dist[pr] = acc_s / S;
+}
+
+void launch_vector_pairs(const double* G, int S, int n, const int* pair_i, const int* pair_j, int npairs, int metric,
+                         double* dist, cudaStream_t st) {
+  vector_pair_kernel<<<npairs, 256, 0, st>>>(G, S, n, pair_i, pair_j, metric, dist);
+  g_launch_count++;
+}
+
 int configure_hellinger_kernels() {
   cudaError_t e = cudaFuncSetAttribute(hellinger_precompute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(HellSmem));

@@ -299,3 +299,95 @@ class HellingerDistanceBuilder(DistanceBuilder):
                                                d_st.data_ptr())
         _lib.check(engine.ctx, rc, 'b200gp_hellinger_pairs')
         return float(d_dist.cpu().numpy()[0])
+
+
+class _VectorInfo(object):
+    """`model.info` of the Frobenius / correlation builders: the reference's (n^2 x S) float32 matrix of vec(K_s + lambda_s I)
+    columns (distance.py:214-232), fetched from HBM on demand."""
+
+    def __init__(self, builder, slot):
+        self.builder, self.slot = builder, slot
+
+    def __array__(self, dtype=None, copy=None):
+        G = self.builder._d_G[self.slot]                         # [S][n][n] float64 on the device
+        v = G.reshape(G.shape[0], -1).t().contiguous().cpu().numpy().astype(np.float32)
+        return v if dtype is None else v.astype(dtype)
+
+
+class _VectorDistanceBuilder(HellingerDistanceBuilder):
+    """Shared machinery of FrobeniusDistanceBuilder / CorrelationDistanceBuilder (distance.py:197-284): the sampled prior
+    Gram matrices are the ones the Hellinger precompute builds; only the pair metric differs."""
+    _metric_code = 0
+
+    def precompute_information(self, active_models, new_candidates_indices, data_X):
+        super(_VectorDistanceBuilder, self).precompute_information(active_models, new_candidates_indices, data_X)
+        for i in [int(i) for i in new_candidates_indices]:
+            active_models.models[i].info = _VectorInfo(self, i)
+
+    def create_precomputed_info(self, covariance, data_X):
+        log_det, G = super(_VectorDistanceBuilder, self).create_precomputed_info(covariance, data_X)
+        n = G.shape[0]
+        return G.reshape(n * n, G.shape[2]).astype(np.float32)
+
+    def pair_distances(self, pair_i, pair_j):
+        torch, eng = self.engine.torch, self.engine
+        pi = np.ascontiguousarray(np.asarray(pair_i, dtype=np.int32))
+        pj = np.ascontiguousarray(np.asarray(pair_j, dtype=np.int32))
+        npairs = int(pi.size)
+        if npairs == 0:
+            return np.zeros(0), np.zeros(0, dtype=np.int32)
+        if max(pi.max(), pj.max()) >= self._capacity:
+            raise ValueError('pair refers to a model without precomputed information')
+        d_pi, d_pj = torch.from_numpy(pi).to(eng.device), torch.from_numpy(pj).to(eng.device)
+        d_dist = torch.empty(npairs, dtype=torch.float64, device=eng.device)
+        rc = eng.lib.b200gp_vector_pairs(eng.ctx, self._d_G.data_ptr(), self._capacity, self.num_samples, self._n,
+                                         d_pi.data_ptr(), d_pj.data_ptr(), npairs, self._metric_code, d_dist.data_ptr())
+        _lib.check(eng.ctx, rc, 'b200gp_vector_pairs')
+        return d_dist.cpu().numpy(), np.zeros(npairs, dtype=np.int32)
+
+    @classmethod
+    def _host_pair(cls, a, b, engine=None):
+        """Distance of two explicit (n^2 x S) vector matrices, evaluated on the device."""
+        if engine is None:
+            from .engine import get_engine
+            engine = get_engine(0, 'distance')
+        torch = engine.torch
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        n2, S = a.shape
+        n = int(round(np.sqrt(n2)))
+        G = np.ascontiguousarray(np.stack([a.T, b.T]))           # [2][S][n^2]
+        d_G = torch.from_numpy(G).to(engine.device)
+        d_pi = torch.zeros(1, dtype=torch.int32, device=engine.device)
+        d_pj = torch.ones(1, dtype=torch.int32, device=engine.device)
+        d_dist = torch.empty(1, dtype=torch.float64, device=engine.device)
+        rc = engine.lib.b200gp_vector_pairs(engine.ctx, d_G.data_ptr(), 2, S, n, d_pi.data_ptr(), d_pj.data_ptr(), 1,
+                                            cls._metric_code, d_dist.data_ptr())
+        _lib.check(engine.ctx, rc, 'b200gp_vector_pairs')
+        return float(d_dist.cpu().numpy()[0])
+
+
+class FrobeniusDistanceBuilder(_VectorDistanceBuilder):
+    """distance.py:197-232: average Frobenius distance between the sampled prior Gram matrices."""
+    _metric_code = 0
+
+    @staticmethod
+    def metric(data_i, data_j, **kwargs):
+        return FrobeniusDistanceBuilder.frobenius_distance(data_i, data_j)
+
+    @staticmethod
+    def frobenius_distance(a, b):
+        return FrobeniusDistanceBuilder._host_pair(a, b)
+
+
+class CorrelationDistanceBuilder(_VectorDistanceBuilder):
+    """distance.py:235-284: average correlation distance sqrt(1/2 (1 - corr)); what SMBOModelSelector wires
+    (src/autoks/core/model_selection/smbo_model_selector.py:91)."""
+    _metric_code = 1
+
+    @staticmethod
+    def metric(data_i, data_j, **kwargs):
+        return CorrelationDistanceBuilder.correlation_distance(data_i, data_j)
+
+    @staticmethod
+    def correlation_distance(a, b):
+        return CorrelationDistanceBuilder._host_pair(a, b)

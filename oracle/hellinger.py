@@ -84,3 +84,24 @@ def distance_matrix(infos, max_n=None):
         for j in range(i + 1, m):
             D[i, j] = D[j, i] = hellinger_distance(*infos[i], *infos[j])
     return D
+
+
+# ---- Frobenius / correlation builders (src/autoks/distance/distance.py:197-284), float32 like the reference ----------
+def create_vectors(expr, kern_priors, data_X, prob_samples, lam, dist_mode='gpy'):
+    """create_precomputed_info of FrobeniusDistanceBuilder / CorrelationDistanceBuilder: (n^2 x S) float32."""
+    _ld, G = create_precomputed_info(expr, kern_priors, data_X, prob_samples, lam, dist_mode)
+    n = G.shape[0]
+    return G.reshape(n * n, G.shape[2]).astype(np.float32)
+
+
+def frobenius_distance(a, b):
+    return float(np.mean(np.sqrt(np.sum((a - b) ** 2, axis=0))))
+
+
+def correlation_distance(a, b):
+    a_centered = a - np.mean(a, axis=0)
+    b_centered = b - np.mean(b, axis=0)
+    dot_prod = np.einsum('ij,ji->i', a_centered.T, b_centered)
+    correlation = dot_prod / (np.linalg.norm(a_centered, axis=0) * np.linalg.norm(b_centered, axis=0))
+    correlation = np.clip(correlation, 0, 1)
+    return float(np.mean(np.sqrt(0.5 * (1 - correlation)), axis=0))
