@@ -124,6 +124,15 @@ int b200gp_hellinger_pairs(b200gp_ctx* ctx, const double* d_logdet, const double
                            const int32_t* d_pair_i, const int32_t* d_pair_j, int npairs, double tol_logdet, void* d_work,
                            double* d_dist, int32_t* d_status);
 
+/* Centred kernel alignment of every pair of the n items ids[0..n) over the bound X (SURVEY.md 8f row f2;
+ * pairwise_centered_alignments -> centered_alignment -> center_kernel / alignment / inner_frob,
+ * src/autoks/core/covariance.py:278-338): d_out[a * n + b] = <HK_aH, HK_bH>_F / sqrt(<HK_aH, HK_aH>_F <HK_bH, HK_bH>_F),
+ * K = kern.K(X) without noise, H = I - 11^T / N.  Needs n <= bound slots (all n kernel matrices are resident);
+ * theta has the b200gp_lml_grad layout (the noise entries are ignored). */
+int b200gp_alignment_min_slots(int N, int n);      /* slots to bind for n kernels of order N (>= n: scratch re-uses slots) */
+int b200gp_centered_alignments(b200gp_ctx* ctx, const int32_t* d_prog, const int32_t* d_prog_off, const double* d_theta,
+                               const int32_t* d_theta_off, const int32_t* d_ids, int n, double* d_out);
+
 /* Frobenius (metric 0) / correlation (metric 1) distance between the sampled prior Gram matrices of model pairs
  * (FrobeniusDistanceBuilder.frobenius_distance / CorrelationDistanceBuilder.correlation_distance,
  * src/autoks/distance/distance.py:208-212,242-265).  d_G is the [M][S][n][n] stack b200gp_hellinger_precompute wrote

@@ -85,3 +85,40 @@ def _postfix_to_symbol(postfix_tokens):
         else:
             stack.append(Symbol(program.leaf_name(t)))
     return stack.pop()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Kernel-matrix diversity metrics (src/autoks/core/covariance.py:278-338).  The reference centres
+# each N x N matrix with two N^3 matmuls per pair; here one device call handles the whole population (csrc/align.cu).
+# ---------------------------------------------------------------------------------------------------------------------
+def pairwise_centered_alignments(covariances, x, engine=None):
+    """Alignment of all pairs of covariances (covariance.py:320-338).  Like the reference, only i < j is computed and
+    the result is `(dists + dists.T) / 2`: off-diagonal entries hold HALF the alignment, the diagonal is 0."""
+    import numpy as np
+    from .program import ProgramBatch
+    n = len(covariances)
+    dists = np.zeros((n, n))
+    if n < 2:
+        return dists
+    if engine is None:
+        from .engine import get_engine
+        engine = get_engine(0, 'metrics')
+    x = np.asarray(x, dtype=np.float64)
+    batch = ProgramBatch([c.raw_kernel for c in covariances])
+    need = engine.lib.b200gp_alignment_min_slots(int(x.shape[0]), n)
+    slots = engine.slots_for(x.shape[0], x.shape[1], need, batch.max_params, mem_fraction=0.85,
+                             extra_bytes=0 if engine._ws is None else engine._ws.numel())
+    if slots < need:
+        raise MemoryError('%d kernel matrices of order %d do not fit on the device at once (%d of %d slots)'
+                          % (n, x.shape[0], slots, need))
+    engine.bind(x, np.zeros(x.shape[0]), need, batch.max_params)
+    engine.upload_programs(batch)
+    A = engine.centered_alignments(batch, batch.initial_theta())
+    iu = np.triu_indices(n, 1)
+    dists[iu] = A[iu]
+    return (dists + dists.T) / 2.
+
+
+def centered_alignment_of_kernels(cov1, cov2, x, engine=None):
+    """centered_alignment(compute_kernel(k1, x), compute_kernel(k2, x)) for two covariances (covariance.py:301-308)."""
+    return 2.0 * float(pairwise_centered_alignments([cov1, cov2], x, engine)[0, 1])

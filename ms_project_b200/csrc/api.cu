@@ -24,6 +24,8 @@ void launch_pack_data(const double* X, const double* y, int N, int D, int Np, do
 void launch_predict(const Batch& b, int item, const double* Xs, int ns, int include_likelihood, double* scratch, double* mean,
                     double* var, cudaStream_t s);
 int configure_predict_kernels();
+int launch_alignments(const Batch& b, int nmodels, double* out, cudaStream_t s);
+int configure_align_kernels();
 }
 
 struct b200gp_ctx {
@@ -132,7 +134,8 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -3;
   if (prop.major < 10) return -4;   // sm_100a only: there is no fallback path
-  if (configure_kernels() != 0 || configure_hellinger_kernels() != 0 || configure_predict_kernels() != 0) return -5;
+  if (configure_kernels() != 0 || configure_hellinger_kernels() != 0 || configure_predict_kernels() != 0 ||
+      configure_align_kernels() != 0) return -5;
   b200gp_ctx* c = new b200gp_ctx();
   c->device = device;
   c->stream = static_cast<cudaStream_t>(cuda_stream);
@@ -595,6 +598,42 @@ int b200gp_hellinger_pairs(b200gp_ctx* c, const double* logdet, const double* G,
   double* h = cv.take<double>((size_t)npairs * S);
   int* hs = cv.take<int>((size_t)npairs * S);
   launch_hellinger_pairs(logdet, G, S, n, pair_i, pair_j, npairs, tol_logdet, h, hs, dist, status, c->stream);
+  CUCHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int b200gp_alignment_min_slots(int N, int n) {
+  if (N <= 0 || n <= 0) return 0;
+  const size_t Np = round_up(N, NB), mp = round_up(n, NB), nsplit = (N + 15) / 16;
+  const size_t for_partials = (nsplit * mp * mp + Np * Np - 1) / (Np * Np);       // split-K partials live in M2
+  const size_t for_products = ((size_t)n * n + (Np / NB) * NB * NB - 1) / ((Np / NB) * NB * NB);   // centred products in Dinv
+  size_t need = (size_t)n;
+  if (for_partials > need) need = for_partials;
+  if (for_products > need) need = for_products;
+  return (int)need;
+}
+
+int b200gp_centered_alignments(b200gp_ctx* c, const int32_t* prog, const int32_t* prog_off, const double* theta,
+                               const int32_t* theta_off, const int32_t* ids, int n, double* out) {
+  if (!c) return -1;
+  if (!c->bound) return fail(c, "b200gp_centered_alignments: call b200gp_bind first");
+  if (!prog || !prog_off || !theta || !theta_off || !ids || !out) return fail(c, "b200gp_centered_alignments: null pointer");
+  if (n <= 0) return 0;
+  if (b200gp_alignment_min_slots(c->base.N, n) > c->slots)
+    return fail(c, "b200gp_centered_alignments: %d kernels of order %d need %d slots, %d are bound", n, c->base.N,
+                b200gp_alignment_min_slots(c->base.N, n), c->slots);
+  CUCHECK(c, cudaSetDevice(c->device));
+  Batch b = c->base;
+  b.nslots = n;
+  b.ids = ids;
+  b.prog = reinterpret_cast<const int4*>(prog); b.prog_off = prog_off; b.theta = theta; b.theta_off = theta_off;
+  b.quirks = c->quirks; b.lut = c->lut; b.lut_n = c->lut_n;
+  b.add_diag = 0;
+  launch_compile(b, c->stream);
+  launch_build_k(b, c->stream);
+  b.nslots = c->slots;            // scratch capacity: every bound slot
+  const int rc = launch_alignments(b, n, out, c->stream);
+  if (rc != 0) return fail(c, "b200gp_centered_alignments: scratch does not fit the bound workspace (code %d)", rc);
   CUCHECK(c, cudaGetLastError());
   return 0;
 }

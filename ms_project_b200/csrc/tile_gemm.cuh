@@ -78,9 +78,10 @@ __device__ __forceinline__ void tg_load_stage(double* stage, const double* __res
 // acc[mt][nt][2]: C fragment of DMMA tile (mt, nt) of this warp's 32 x 32 sub-tile.
 // Element (row, col) of the CTA tile held in acc[mt][nt][e]:
 //   row = wm*32 + mt*8 + (lane>>2),  col = wn*32 + nt*8 + (lane&3)*2 + e
-__device__ __forceinline__ void tile_gemm_nt(double (&acc)[TG_MT][TG_NT][2], const double* __restrict__ A, size_t lda,
-                                             const double* __restrict__ B, size_t ldb, int nchunks, double* smem,
-                                             int kc_lo = 0, int kc_hi = 1 << 30) {
+// `load(stage, chunk)` issues the cp.async copies of K-chunk `chunk` (128 A rows, 64 B rows, 16 doubles each) into `stage`.
+template <typename Loader>
+__device__ __forceinline__ void tile_gemm_pipeline(double (&acc)[TG_MT][TG_NT][2], Loader load, int nchunks, double* smem,
+                                                   int kc_lo = 0, int kc_hi = 1 << 30) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int wm, wn;
   warp_coords(warp, wm, wn);
@@ -90,7 +91,7 @@ __device__ __forceinline__ void tile_gemm_nt(double (&acc)[TG_MT][TG_NT][2], con
 
 #pragma unroll
   for (int s = 0; s < TG_STAGES - 1; s++) {
-    if (s < nchunks) tg_load_stage(smem + s * TG_STAGE_DOUBLES, A, lda, B, ldb, s * TG_KC);
+    if (s < nchunks) load(smem + s * TG_STAGE_DOUBLES, s);
     cp_async_commit();
   }
   cp_async_wait<TG_STAGES - 2>();
@@ -104,7 +105,7 @@ __device__ __forceinline__ void tile_gemm_nt(double (&acc)[TG_MT][TG_NT][2], con
   for (int kc = 0; kc < nchunks; kc++) {
     {   // refill the stage chunk kc-1 was read from: every warp passed the barrier of the previous iteration
       const int nk = kc + TG_STAGES - 1;
-      if (nk < nchunks) tg_load_stage(smem + (nk % TG_STAGES) * TG_STAGE_DOUBLES, A, lda, B, ldb, nk * TG_KC);
+      if (nk < nchunks) load(smem + (nk % TG_STAGES) * TG_STAGE_DOUBLES, nk);
       cp_async_commit();
     }
     const double* As = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + aoff;
@@ -141,6 +142,14 @@ __device__ __forceinline__ void tile_gemm_nt(double (&acc)[TG_MT][TG_NT][2], con
     }
   }
   cp_async_wait<0>();
+}
+
+// Contiguous-K form: chunk kc starts at column 16 kc of both operands.
+__device__ __forceinline__ void tile_gemm_nt(double (&acc)[TG_MT][TG_NT][2], const double* __restrict__ A, size_t lda,
+                                             const double* __restrict__ B, size_t ldb, int nchunks, double* smem,
+                                             int kc_lo = 0, int kc_hi = 1 << 30) {
+  tile_gemm_pipeline(acc, [=](double* stage, int chunk) { tg_load_stage(stage, A, lda, B, ldb, chunk * TG_KC); }, nchunks,
+                     smem, kc_lo, kc_hi);
 }
 
 }  // namespace b200gp

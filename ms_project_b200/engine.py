@@ -222,6 +222,19 @@ class Engine(object):
         _lib.check(self.ctx, rc, 'b200gp_build_K')
         return out.cpu().numpy()
 
+    def centered_alignments(self, batch, theta):
+        """Centred alignment of every pair of an uploaded batch's kernels over the bound X: n x n, diagonal 1."""
+        torch = self.torch
+        n = batch.n_items
+        batch.h_theta.numpy()[:] = theta
+        batch.d_theta.copy_(batch.h_theta, non_blocking=True)
+        out = torch.empty((n, n), dtype=torch.float64, device=self.device)
+        rc = self.lib.b200gp_centered_alignments(self.ctx, batch.d_tokens.data_ptr(), batch.d_prog_off.data_ptr(),
+                                                 batch.d_theta.data_ptr(), batch.d_theta_off.data_ptr(),
+                                                 batch.d_all_ids.data_ptr(), n, out.data_ptr())
+        _lib.check(self.ctx, rc, 'b200gp_centered_alignments')
+        return out.cpu().numpy()
+
     def potrf(self, A):
         """In-place blocked Cholesky of a device tensor A (N x N float64, N % 128 == 0).
         Returns (logdet, status)."""
