@@ -115,6 +115,20 @@ def c3(eng, budget):
     dist, status = builder.pair_distances(ii, jj)
     torch.cuda.synchronize()
     t_pairs = time.perf_counter() - t0
+    # the distance SMBO actually wires (CorrelationDistanceBuilder, smbo_model_selector.py:91): same sampled Gram stack
+    from ms_project_b200.distance import CorrelationDistanceBuilder
+    cb = CorrelationDistanceBuilder(noise_prior, 20, 40, n, am, list(range(n)), xsub, probability_samples_matrix=prob, engine=eng)
+    cb.pair_distances(ii[:1000], jj[:1000])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cdist_, _ = cb.pair_distances(ii, jj)
+    torch.cuda.synchronize()
+    t_corr = time.perf_counter() - t0
+    v0, v1 = np.asarray(am.models[0].info), np.asarray(am.models[7].info)
+    c0 = time.perf_counter()
+    for _ in range(20):
+        ohell.correlation_distance(v0, v1)
+    c_corr = (time.perf_counter() - c0) / 20
     # CPU sample
     lam = ohell.noise_samples(prior_tuple(noise_prior), prob)
     c0 = time.perf_counter()
@@ -136,6 +150,9 @@ def c3(eng, budget):
             'pairs_per_s': ii.size / t_pairs, 'pair_sample_choleskys_per_s': ii.size * 20 / t_pairs,
             'fp64_gflops_pairs': ii.size * 20 * (100 ** 3 / 3.0) / t_pairs / 1e9,
             'nan_distances': int(np.isnan(dist).sum()), 'bad_status': int((status != 0).sum()),
+            'correlation_pairs_seconds': t_corr, 'correlation_pairs_per_s': ii.size / t_corr,
+            'correlation_effective_GBps': ii.size * 2 * 20 * 100 * 100 * 8 / t_corr / 1e9,
+            'correlation_cpu_seconds_per_pair': c_corr, 'correlation_nan': int(np.isnan(cdist_).sum()),
             'cpu': {'kind': 'port', 'precompute_seconds_per_model': c_pre, 'seconds_per_pair': c_pair, 'pairs_timed': npair,
                     'pairs_per_s': 1.0 / c_pair, 'projected_seconds_all_pairs': c_pair * ii.size + c_pre * n}}
 
@@ -173,10 +190,29 @@ def c4(eng, budget):
         if time.perf_counter() - c0 > budget:
             break
     cdt = time.perf_counter() - c0
+    # population diversity statistic of every generation (pairwise centred alignment, covariance.py:320-338)
+    from ms_project_b200.covariance import Covariance, pairwise_centered_alignments
+    from oracle import kernels as okern, scoring as osc
+    covs = [Covariance(k) for k in kernels]
+    pairwise_centered_alignments(covs[:8], X, engine=eng)
+    torch.cuda.synchronize()
+    a0 = time.perf_counter()
+    A = pairwise_centered_alignments(covs, X, engine=eng)
+    torch.cuda.synchronize()
+    t_align = time.perf_counter() - a0
+    K0 = okern.K(to_oracle_expr(kernels[0]), kernels[0].param_array, X, None, 'direct')
+    K1 = okern.K(to_oracle_expr(kernels[1]), kernels[1].param_array, X, None, 'direct')
+    a0 = time.perf_counter()
+    ref01 = osc.centered_alignment(K0, K1)
+    c_align = time.perf_counter() - a0
+    npairs = batch.n_items * (batch.n_items - 1) // 2
+    align = {'seconds_all_pairs': t_align, 'pairs': npairs, 'fp64_tflops_gram': npairs * float(N) ** 2 / t_align / 1e12,
+             'parity_pair01_abs_err': abs(2 * A[0, 1] - ref01), 'cpu_seconds_per_pair': c_align,
+             'cpu_projected_seconds_all_pairs': c_align * npairs}
     return {'config': 'C4 evalg population 512, D=8, N=4096: NLML+grad of every candidate (one generation step)',
             'items': batch.n_items, 'slots': slots, 'seconds': dt, 'evaluations_per_s': batch.n_items / dt,
             'fp64_tflops': batch.n_items * float(N) ** 3 / dt / 1e12, 'status_counts': np.bincount(status, minlength=4).tolist(),
-            'parity_checked_items': n_cpu,
+            'parity_checked_items': n_cpu, 'centered_alignments': align,
             'cpu': {'kind': 'port', 'items': n_cpu, 'seconds': cdt, 'evaluations_per_s': n_cpu / cdt}}
 
 
