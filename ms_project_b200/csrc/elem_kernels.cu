@@ -201,61 +201,68 @@ __device__ __forceinline__ void leaf_fwd(int op, unsigned cst, const double (&Ar
   }
 }
 
-// acc[p] += sum_e g[e] dv/dtheta_p for the leaf's own parameters (same formulas as kprog.cuh eval_grad).
+// acc[p] += sum_e g[e] * (the element-dependent factor of dv/dtheta_p); the per-leaf constant factors are applied
+// once per tile by leaf_grad_scale (same formulas as kprog.cuh eval_grad, constants hoisted out of the N^2 loop).
 template <int E>
-__device__ __forceinline__ void leaf_bwd(int op, unsigned cst, double ivar, const double (&Ar)[E], unsigned srow, unsigned crow,
+__device__ __forceinline__ void leaf_bwd(int op, unsigned cst, const double (&Ar)[E], unsigned srow, unsigned crow,
                                          double Aj, double Sj, double Cj, const double (&g)[E], const double (&v)[E],
-                                         const double (&aux)[E], double (&acc)[3], int quirks) {
-  if (op == OP_SE) {
-    const double c1 = lds_f64(cst + 8);
+                                         const double (&aux)[E], double (&acc)[3]) {
+  if (op == OP_SE) {            // dK/dv = K / v ; dK/dl = K r^2 / l
 #pragma unroll
     for (int e = 0; e < E; e++) {
       const double gv = g[e] * v[e];
-      acc[0] = fma(gv, ivar, acc[0]);
-      acc[1] = fma(gv, aux[e] * c1, acc[1]);
+      acc[0] += gv;
+      acc[1] = fma(gv, aux[e], acc[1]);
     }
-  } else if (op == OP_RQ) {
-    const double c1 = lds_f64(cst + 8);
-    double c2, c3;
-    lds_v2(cst + 16, c2, c3);
+  } else if (op == OP_RQ) {     // rational-quadratic.ipynb#2
+    double c1, c3;
+    c1 = lds_f64(cst + 8);
+    c3 = lds_f64(cst + 24);
 #pragma unroll
     for (int e = 0; e < E; e++) {
       const double r = (Ar[e] - Aj) * c1;
       const double u = (r * r) * c3;
-      const double e1 = rcp_sl(1.0 + u);
+      const double ue = u * rcp_sl(1.0 + u);
       const double gv = g[e] * v[e];
-      acc[0] = fma(gv, ivar, acc[0]);
-      acc[1] = fma(gv, (u * (2.0 * c2)) * c1 * e1, acc[1]);
-      acc[2] = fma(gv, u * e1 - aux[e], acc[2]);
+      acc[0] += gv;
+      acc[1] = fma(gv, ue, acc[1]);
+      acc[2] = fma(gv, ue - aux[e], acc[2]);
     }
-  } else if (op == OP_PER) {
-    double il, ip;
-    lds_v2(cst + 16, il, ip);
-    const double lsf = (quirks & QUIRK_PER_LENGTHSCALE) ? 1.0 : 4.0;
+  } else if (op == OP_PER) {    // periodic.ipynb#2
     double Sr[E], Cr[E];
     lds_rows<E>(srow, Sr);
     lds_rows<E>(crow, Cr);
 #pragma unroll
     for (int e = 0; e < E; e++) {
       const double s = aux[e];
-      const double c = Cr[e] * Cj + Sr[e] * Sj;
-      const double base = Ar[e] - Aj;
-      const double q = s * il;
+      const double c = fma(Cr[e], Cj, Sr[e] * Sj);
       const double gv = g[e] * v[e];
-      acc[0] = fma(gv, ivar, acc[0]);
-      acc[1] = fma(gv, (4.0 * il * il) * s * c * (base * ip), acc[1]);
-      acc[2] = fma(gv, lsf * (q * q) * il, acc[2]);
+      acc[0] += gv;
+      acc[1] = fma(gv * s, c * (Ar[e] - Aj), acc[1]);
+      acc[2] = fma(gv * s, s, acc[2]);
     }
-  } else if (op == OP_LIN) {
-    const double sf = (quirks & QUIRK_LIN_SHIFT) ? 1.0 : lds_f64(cst);
+  } else if (op == OP_LIN) {    // linear.ipynb#2
 #pragma unroll
     for (int e = 0; e < E; e++) {
       acc[0] = fma(g[e], aux[e], acc[0]);
-      acc[1] = fma(g[e], sf * (-(Ar[e] + Aj)), acc[1]);
+      acc[1] = fma(g[e], Ar[e] + Aj, acc[1]);
     }
   } else {
 #pragma unroll
     for (int e = 0; e < E; e++) acc[0] += g[e];
+  }
+}
+
+// constant factor of parameter p of a leaf: dL/dtheta_p = scale * accumulated sum
+__device__ __forceinline__ double leaf_grad_scale(int op, const double* cst, double ivar, int p, int quirks) {
+  switch (op) {
+    case OP_SE:  return p == 0 ? ivar : cst[1];
+    case OP_RQ:  return p == 0 ? ivar : (p == 1 ? 2.0 * cst[2] * cst[1] : 1.0);
+    case OP_PER: return p == 0 ? ivar
+                        : (p == 1 ? 4.0 * cst[2] * cst[2] * cst[3]
+                                  : ((quirks & QUIRK_PER_LENGTHSCALE) ? 1.0 : 4.0) * cst[2] * cst[2] * cst[2]);
+    case OP_LIN: return p == 0 ? 1.0 : -((quirks & QUIRK_LIN_SHIFT) ? 1.0 : cst[0]);
+    default:     return 1.0;
   }
 }
 
@@ -474,9 +481,8 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_grad_kernel(Batch
           }
           double Ar[E];
           lds_rows<E>(sb + (unsigned)offsetof(SM, Ai) + (l * NB + r0) * 8, Ar);
-          leaf_bwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, lds_f64(sb + (unsigned)offsetof(SM, ivar) + l * 8), Ar,
-                      sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8, sb + (unsigned)offsetof(SM, Ci) + (l * NB + r0) * 8,
-                      Aj[l], Sj[l], Cj[l], g, v[l], aux[l], acc[l], b.quirks);
+          leaf_bwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, Ar, sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8,
+                      sb + (unsigned)offsetof(SM, Ci) + (l * NB + r0) * 8, Aj[l], Sj[l], Cj[l], g, v[l], aux[l], acc[l]);
         }
     }
     // CTA reduction in a fixed order: lanes (shuffle tree), then the 8 warps
@@ -497,7 +503,8 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_grad_kernel(Batch
       if (i == NV - 1) out[S.cp.nparam] = s;
       else {
         const int l = i / 3, p = i % 3;
-        if (l < L && p < S.cp.leaf[l].w) out[S.cp.leaf[l].z + p] = s;
+        if (l < L && p < S.cp.leaf[l].w)
+          out[S.cp.leaf[l].z + p] = s * leaf_grad_scale(S.cp.leaf[l].x, S.cst[l], S.ivar[l], p, b.quirks);
       }
     }
   }

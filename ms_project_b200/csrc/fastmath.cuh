@@ -37,24 +37,19 @@ __device__ __forceinline__ double exp_sl(double x) {
   const double fn = t - FM_C[1];
   double r = fma(fn, FM_C[2], x);
   r = fma(fn, FM_C[3], r);
-  // exp(r), |r| <= ln2 / 2: Taylor to r^13 (remainder 4e-18 relative), Estrin's scheme: dependency depth 5 instead
-  // of Horner's 14, which is what a latency-bound kernel needs (3 extra multiplies)
+  // exp(r), |r| <= ln2 / 2: Taylor to r^13 (remainder 4e-18 relative) as even(r^2) + r odd(r^2): two Horner chains of
+  // depth 7 with ONE constant operand per DFMA (Estrin's pairs need two, i.e. an extra LDC each); with the two elements
+  // a thread interleaves that is four independent chains
   const double r2 = r * r;
-  const double a0 = fma(r, FM_C[4], FM_C[4]);          // 1 + r
-  const double a1 = fma(r, FM_EXP[10], FM_EXP[11]);    // 1/2! + r/3!
-  const double a2 = fma(r, FM_EXP[8], FM_EXP[9]);
-  const double a3 = fma(r, FM_EXP[6], FM_EXP[7]);
-  const double a4 = fma(r, FM_EXP[4], FM_EXP[5]);
-  const double a5 = fma(r, FM_EXP[2], FM_EXP[3]);
-  const double a6 = fma(r, FM_EXP[0], FM_EXP[1]);      // 1/12! + r/13!
-  const double r4 = r2 * r2;
-  const double b0 = fma(a1, r2, a0);
-  const double b1 = fma(a3, r2, a2);
-  const double b2 = fma(a5, r2, a4);
-  const double r8 = r4 * r4;
-  const double d0 = fma(b1, r4, b0);
-  const double d1 = fma(a6, r4, b2);
-  const double p = fma(d1, r8, d0);
+  double pe = FM_EXP[1];                      // 1/12!
+  double po = FM_EXP[0];                      // 1/13!
+  pe = fma(pe, r2, FM_EXP[3]); po = fma(po, r2, FM_EXP[2]);      // 1/10!, 1/11!
+  pe = fma(pe, r2, FM_EXP[5]); po = fma(po, r2, FM_EXP[4]);      // 1/8!,  1/9!
+  pe = fma(pe, r2, FM_EXP[7]); po = fma(po, r2, FM_EXP[6]);      // 1/6!,  1/7!
+  pe = fma(pe, r2, FM_EXP[9]); po = fma(po, r2, FM_EXP[8]);      // 1/4!,  1/5!
+  pe = fma(pe, r2, FM_EXP[11]); po = fma(po, r2, FM_EXP[10]);    // 1/2!,  1/3!
+  pe = fma(pe, r2, FM_C[4]); po = fma(po, r2, FM_C[4]);          // 1,     1
+  const double p = fma(po, r, pe);
   // p * 2^n by exponent arithmetic (normal range).  x < -708 flushes to (sub)zero -- the test is on x itself because
   // the magic-number rounding above only holds n for |x| < 1.5e15 (tiny lengthscales reach far beyond that).  A NaN x
   // gives t = r = p = NaN with n = 0, so it passes through untouched.  x > 709 is outside the domain (the leaf
@@ -75,18 +70,15 @@ __device__ __forceinline__ double log1p_pos(double u) {
   const double f = __hiloint2double(hi, __double2loint(m));
   const double s = (f - 1.0) * rcp_sl(f + 1.0);      // log f = 2 atanh s, |s| <= 0.1716
   const double z = s * s;
-  // q = z (2/3 + 2/5 z + ... + 2/19 z^8), Estrin
+  // q = z (2/3 + 2/5 z + ... + 2/19 z^8) as even(z^2) + z odd(z^2), one constant operand per DFMA
   const double z2 = z * z;
-  const double a0 = fma(z, FM_LOG[7], FM_LOG[8]);
-  const double a1 = fma(z, FM_LOG[5], FM_LOG[6]);
-  const double a2 = fma(z, FM_LOG[3], FM_LOG[4]);
-  const double a3 = fma(z, FM_LOG[1], FM_LOG[2]);
-  const double z4 = z2 * z2;
-  const double b0 = fma(a1, z2, a0);
-  const double b1 = fma(a3, z2, a2);
-  const double z8 = z4 * z4;
-  const double d0 = fma(b1, z4, b0);
-  const double q = fma(FM_LOG[0], z8, d0) * z;
+  double qe = FM_LOG[0];                      // 2/19 (z^8)
+  double qo = FM_LOG[1];                      // 2/17 (z^7)
+  qe = fma(qe, z2, FM_LOG[2]); qo = fma(qo, z2, FM_LOG[3]);      // 2/15 (z^6), 2/13 (z^5)
+  qe = fma(qe, z2, FM_LOG[4]); qo = fma(qo, z2, FM_LOG[5]);      // 2/11 (z^4), 2/9 (z^3)
+  qe = fma(qe, z2, FM_LOG[6]); qo = fma(qo, z2, FM_LOG[7]);      // 2/7 (z^2),  2/5 (z)
+  qe = fma(qe, z2, FM_LOG[8]);                                   // 2/3
+  const double q = fma(qo, z, qe) * z;
   const double lf = fma(s, q, s + s);
   const double fe = (double)e;
   const double res = fma(fe, -FM_C[2], fma(fe, -FM_C[3], lf));
