@@ -5,6 +5,7 @@ TAG=${1:-r01}
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu_$TAG.log
+python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$TAG.log 2>&1; echo "smoke rc=$?" | tee -a $O/smoke_$TAG.log
 tail -3 $O/pytest_gpu_$TAG.log
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu --no-fit"
 $BENCH > $O/bench_plain_$TAG.json 2> $O/bench_plain_$TAG.err && \
@@ -14,7 +15,7 @@ $PROBE > $O/probe_plain_$TAG.log 2>&1 || exit 1
 cap() {  # name, kernel regex, skip
   ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o $O/prof_$1_$TAG $PROBE > $O/ncu_$1_$TAG.log 2>&1
 }
-cap upd chol_update_kernel 1
+cap upd chol_update_kernel 3      # 4th launch = the K = 512 trailing update of the first panel (slot group 0)
 cap vupd inv_update_kernel 3
 cap kinv kinv_kernel 0
 cap trsm chol_trsm_kernel 2
