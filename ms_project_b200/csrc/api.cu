@@ -11,7 +11,7 @@
 using namespace b200gp;
 
 namespace b200gp {
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 int configure_hellinger_kernels();
 void launch_hellinger_precompute(const double* Xsub, int n, int D, const int4* prog, const int* prog_off,
                                  const double* theta, const int* theta_off, const double* lambda, int M, int S,
@@ -196,7 +196,7 @@ int b200gp_set_profiling(b200gp_ctx* c, int enabled) {
   return 0;
 }
 
-long long b200gp_launch_count(b200gp_ctx*) { return g_launch_count; }
+long long b200gp_launch_count(b200gp_ctx*) { return g_launch_count.load(); }
 
 int b200gp_last_phase_ms(b200gp_ctx* c, float* out, int cap) {
   if (!c || !out) return -1;

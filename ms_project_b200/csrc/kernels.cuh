@@ -1,5 +1,6 @@
 // Internal launch interface between the C-ABI layer (api.cu) and the kernel translation units.
 #pragma once
+#include <atomic>
 #include "common.cuh"
 #include "cprog.cuh"
 
@@ -67,6 +68,6 @@ void launch_solve(const Batch& b, cudaStream_t s);                          // z
 void launch_grad(const Batch& b, cudaStream_t s);
 void launch_finalize(const Batch& b, int with_grad, cudaStream_t s);
 int configure_kernels();
-extern long long g_launch_count;                                            // kernels launched (host-side counter)                                                    // opt-in shared memory sizes
+extern std::atomic<long long> g_launch_count;                                            // kernels launched (host-side counter)                                                    // opt-in shared memory sizes
 
 }  // namespace b200gp

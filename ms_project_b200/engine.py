@@ -20,13 +20,17 @@ def _torch():
 class Engine(object):
     """One per GPU.  `bind` the (standardised) training data once per search, then score batches."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, own_stream=False):
         torch = _torch()
         self.torch = torch
         self.device = torch.device('cuda', device)
         self.lib = _lib.lib()
         torch.cuda.set_device(self.device)
-        self.stream = torch.cuda.current_stream(self.device)
+        # own_stream: a private non-blocking stream, so that two engines driven from two host threads overlap on the GPU
+        # (fit.fit_models_overlapped); otherwise everything is enqueued on torch's current stream
+        self.own_stream = bool(own_stream)
+        self.stream = torch.cuda.Stream(self.device) if own_stream else torch.cuda.current_stream(self.device)
+        self._peer = None
         ctx = ctypes.c_void_p()
         rc = self.lib.b200gp_create(device, ctypes.c_void_p(self.stream.cuda_stream), ctypes.byref(ctx))
         if rc != 0:
@@ -38,6 +42,17 @@ class Engine(object):
         self._ws = None
         self._X = self._y = None
         self._X_host = self._y_host = None
+
+    def on_stream(self):
+        """Context manager: torch work issued inside runs on this engine's stream."""
+        import contextlib
+        return self.torch.cuda.stream(self.stream) if self.own_stream else contextlib.nullcontext()
+
+    def peer(self):
+        """A second engine on the same GPU with its own stream and workspace (created on first use)."""
+        if self._peer is None:
+            self._peer = Engine(self.device.index, own_stream=True)
+        return self._peer
 
     def close(self):
         if getattr(self, 'ctx', None):
@@ -72,7 +87,7 @@ class Engine(object):
         budget = int(free * mem_fraction) - fixed
         return int(max(1, min(n_items, budget // max(per_slot, 1))))
 
-    def bind(self, X, y, slots, max_params=32):
+    def _bind_impl(self, X, y, slots, max_params=32):
         """X: N x D, y: N or N x 1 (host numpy, already standardised by the caller)."""
         torch = self.torch
         X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
@@ -109,7 +124,7 @@ class Engine(object):
         self.bind(X, yv, max(want, 1), max(max_params, self.max_params if same else 1))
 
     # ------------------------------------------------------------------ program staging
-    def upload_programs(self, batch):
+    def _upload_programs_impl(self, batch):
         """ProgramBatch -> device tensors (kept on the batch object)."""
         torch = self.torch
         if batch.max_params > self.max_params:
@@ -140,7 +155,7 @@ class Engine(object):
         return batch
 
     # ------------------------------------------------------------------ scoring
-    def lml_grad(self, batch, theta, ids=None, with_grad=True):
+    def _lml_grad_impl(self, batch, theta, ids=None, with_grad=True):
         """Evaluate items `ids` (default: all) of an uploaded batch at the flat host `theta`
         (device layout, see ProgramBatch.pack_theta).  Host buffers in, host results out:
         returns (lml[n_items], dlml[theta layout], status[n_items], tries[n_items]); entries of items not
@@ -171,7 +186,7 @@ class Engine(object):
         ints = batch.h_int.numpy()
         return out[:n], out[n:], ints[:n], ints[n:]
 
-    def lml_grad_device(self, batch, ids=None, with_grad=True):
+    def _lml_grad_device_impl(self, batch, ids=None, with_grad=True):
         """Same evaluation with theta already in `batch.d_theta`; results stay on the device
         (batch.d_out / batch.d_int).  Used by bench.py for the HBM-resident timing."""
         n = batch.n_items
@@ -185,7 +200,7 @@ class Engine(object):
                                       batch.d_int[:n].data_ptr(), batch.d_int[n:].data_ptr())
         _lib.check(self.ctx, rc, 'b200gp_lml_grad')
 
-    def posterior(self, batch, theta, item, Xs, include_likelihood=True):
+    def _posterior_impl(self, batch, theta, item, Xs, include_likelihood=True):
         """GP.predict of item `item` of an uploaded batch at the flat host `theta`: (mean[Ns], var[Ns], lml, status)."""
         torch = self.torch
         Xs = np.ascontiguousarray(np.asarray(Xs, dtype=np.float64))
@@ -204,7 +219,7 @@ class Engine(object):
         out = d_out.cpu().numpy()
         return out[:ns].copy(), out[ns:].copy(), float(batch.d_lml[item].item()), int(batch.d_status[item].item())
 
-    def build_K(self, batch, theta, ids=None, add_diag=False):
+    def _build_K_impl(self, batch, theta, ids=None, add_diag=False):
         """Dense kernel matrices (n x N x N, host numpy) of the selected items over the bound X."""
         torch = self.torch
         batch.h_theta.numpy()[:] = theta
@@ -222,7 +237,7 @@ class Engine(object):
         _lib.check(self.ctx, rc, 'b200gp_build_K')
         return out.cpu().numpy()
 
-    def centered_alignments(self, batch, theta):
+    def _centered_alignments_impl(self, batch, theta):
         """Centred alignment of every pair of an uploaded batch's kernels over the bound X: n x n, diagonal 1."""
         torch = self.torch
         n = batch.n_items
@@ -235,7 +250,7 @@ class Engine(object):
         _lib.check(self.ctx, rc, 'b200gp_centered_alignments')
         return out.cpu().numpy()
 
-    def potrf(self, A):
+    def _potrf_impl(self, A):
         """In-place blocked Cholesky of a device tensor A (N x N float64, N % 128 == 0).
         Returns (logdet, status)."""
         torch = self.torch
@@ -249,6 +264,41 @@ class Engine(object):
         rc = self.lib.b200gp_potrf(self.ctx, A.data_ptr(), N, work.data_ptr(), ctypes.byref(ld), ctypes.byref(st))
         _lib.check(self.ctx, rc, 'b200gp_potrf')
         return ld.value, st.value
+
+
+
+    # ------------------------------------------------------------------ stream-scoped public entry points
+    def bind(self, *args, **kwargs):
+        with self.on_stream():
+            return self._bind_impl(*args, **kwargs)
+
+    def upload_programs(self, *args, **kwargs):
+        with self.on_stream():
+            return self._upload_programs_impl(*args, **kwargs)
+
+    def lml_grad(self, *args, **kwargs):
+        with self.on_stream():
+            return self._lml_grad_impl(*args, **kwargs)
+
+    def lml_grad_device(self, *args, **kwargs):
+        with self.on_stream():
+            return self._lml_grad_device_impl(*args, **kwargs)
+
+    def posterior(self, *args, **kwargs):
+        with self.on_stream():
+            return self._posterior_impl(*args, **kwargs)
+
+    def build_K(self, *args, **kwargs):
+        with self.on_stream():
+            return self._build_K_impl(*args, **kwargs)
+
+    def centered_alignments(self, *args, **kwargs):
+        with self.on_stream():
+            return self._centered_alignments_impl(*args, **kwargs)
+
+    def potrf(self, *args, **kwargs):
+        with self.on_stream():
+            return self._potrf_impl(*args, **kwargs)
 
 
 def get_engine(device=0, role='search'):

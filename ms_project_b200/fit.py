@@ -230,6 +230,42 @@ def fit_models(engine, kernels, likelihoods, num_restarts=10, max_iters=1000, ro
     return results
 
 
+def fit_models_overlapped(engines, kernels, likelihoods, num_restarts=10, max_iters=1000, robust=True, starts=None):
+    """fit_models with the models split into len(engines) contiguous groups, each driven by its own host thread against
+    its own engine (same GPU, private streams): while one group's L-BFGS-B steps run on the host (scipy holds the GIL),
+    the other group's LML+gradient batch runs on the device (ctypes releases the GIL), and the tails of the two groups
+    fill each other's idle SMs.  Results are identical to fit_models: every instance is an independent optimisation, the
+    restart points are drawn up front in the reference's order, and no reduction depends on the batch composition."""
+    M = len(kernels)
+    engines = list(engines)
+    if len(engines) < 2 or M < 2 * len(engines):
+        return fit_models(engines[0], kernels, likelihoods, num_restarts=num_restarts, max_iters=max_iters, robust=robust,
+                          starts=starts)
+    import threading
+    per_model = draw_starts(kernels, likelihoods, int(num_restarts)) if starts is None else starts
+    bounds = np.linspace(0, M, len(engines) + 1).astype(int)
+    results = [None] * len(engines)
+    errors = []
+
+    def run(g):
+        lo, hi = int(bounds[g]), int(bounds[g + 1])
+        try:
+            results[g] = fit_models(engines[g], kernels[lo:hi], likelihoods[lo:hi], num_restarts=num_restarts,
+                                    max_iters=max_iters, robust=robust, starts=per_model[lo:hi])
+        except BaseException as exc:          # re-raised in the caller's thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=run, args=(g,)) for g in range(1, len(engines))]
+    for t in threads:
+        t.start()
+    run(0)
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return [r for part in results for r in part]
+
+
 def _segment_mask(off, items, size):
     mask = np.zeros(size, dtype=bool)
     for j in items:

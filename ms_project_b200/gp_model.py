@@ -12,7 +12,7 @@ from time import time
 import numpy as np
 
 from .covariance import Covariance
-from .fit import fit_models, check_optimizer
+from .fit import fit_models, fit_models_overlapped, check_optimizer
 from .gpy_compat.gp import GP
 from .gpy_compat.likelihoods import Likelihood
 
@@ -114,7 +114,7 @@ def plan_evaluation(models, n_evals, eval_budget, visited, skip_evaluated=True):
 
 
 def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engine=None, model_dict=None,
-                 all_models=None, shard=None):
+                 all_models=None, shard=None, overlap=None):
     """GPModel.score_model for a whole list in ONE lock-step GPU batch (same per-model results and side effects as
     calling score_model on each, including the retry-once rule and failed_fitting)."""
     check_optimizer(optimizer)
@@ -139,14 +139,27 @@ def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engi
         _prepare(m, model_dict)
         gps.append(m.build_model(x, y))
     maxp = max(g.kern.size for g in gps)
-    engine.ensure_bound(x, y, len(gps) * max(int(n_restarts), 1), maxp)
-    results = fit_models(engine, [g.kern for g in gps], [g.likelihood for g in gps], num_restarts=n_restarts, robust=True,
-                         starts=starts)
+    n_inst = len(gps) * max(int(n_restarts), 1)
+    if overlap is None:
+        overlap = len(gps) >= 16         # enough instances for two lock-step drivers to keep the GPU busy
+    if overlap:
+        # two host threads, two engines on the same GPU (fit.fit_models_overlapped): host L-BFGS-B work of one group
+        # hides behind the device batch of the other
+        engines = [engine, engine.peer()]
+        for e in engines:
+            e.ensure_bound(x, y, (n_inst + 1) // 2, maxp)
+        results = fit_models_overlapped(engines, [g.kern for g in gps], [g.likelihood for g in gps], num_restarts=n_restarts,
+                                        robust=True, starts=starts)
+    else:
+        engine.ensure_bound(x, y, n_inst, maxp)
+        results = fit_models(engine, [g.kern for g in gps], [g.likelihood for g in gps], num_restarts=n_restarts, robust=True,
+                             starts=starts)
     for g, r in zip(gps, results):
         g._lml, g._status = r.lml, r.status
         g.optimization_runs += r.runs
     retry = [i for i, g in enumerate(gps) if _is_bad(g.log_likelihood())]
     if retry:
+        engine.ensure_bound(x, y, len(retry) * max(int(n_restarts), 1), maxp)
         rr = fit_models(engine, [gps[i].kern for i in retry], [gps[i].likelihood for i in retry], num_restarts=n_restarts,
                         robust=True)
         for i, r in zip(retry, rr):

@@ -143,3 +143,26 @@ def test_batched_evaluator_replays_reference_loop(engine):
     assert log[0] == 'all_begin' and log[-1] == 'all_end:4' and log.count('begin:LIN_1') == 1 and 'end:LIN_1' not in log
     # a second call is a no-op within the budget
     assert ev.evaluate_models(models, X, y, eval_budget=4) == []
+
+
+def test_overlapped_fit_is_identical_to_single_driver(engine):
+    """Two host threads / two engines on one GPU (fit.fit_models_overlapped) give bit-identical fits: every instance is an
+    independent optimisation and no device reduction depends on the batch composition."""
+    from ms_project_b200 import fitness, workloads
+    from ms_project_b200.covariance import Covariance
+    from ms_project_b200.gp_model import GPModel, score_models
+    from ms_project_b200.gp_models import gp_regression
+    X, y = make_data(140, 2, seed=13)
+    hp = workloads.boms_hyperpriors()
+    bases = workloads.get_all_1d_kernels(['SE', 'RQ'], 2, hp)
+    pool = (bases + workloads.expand_full_brute_force(bases, 1, 40))[:18]
+    md = gp_regression(likelihood_hyperprior={'variance': hp['GP']['variance']})
+    out = []
+    for overlap in (False, True):
+        models = [GPModel(Covariance(k.copy())) for k in pool]
+        np.random.seed(5)
+        scores = score_models(models, X, y, fitness.negative_bic, n_restarts=2, engine=engine, model_dict=md, overlap=overlap)
+        out.append((np.array(scores), [m.fit_result.theta.copy() for m in models], [m.fit_result.n_evals for m in models]))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert all(np.array_equal(a, b) for a, b in zip(out[0][1], out[1][1]))
+    assert out[0][2] == out[1][2]
