@@ -38,7 +38,7 @@ struct b200gp_ctx {
   Batch base{};             // geometry + workspace pointers
   int slots = 0, max_params = 0;
   int panel_tiles = 4;          // look-ahead Cholesky (single large matrix)
-  int batch_panel_tiles = 4;    // batched Cholesky
+  int batch_panel_tiles = 8;    // batched Cholesky / L^-T (measured: 4 -> 26.6, 8 -> 26.2 ms per 256 items at N = 2048)
   double* ws_jitter = nullptr;
   int* ws_ids = nullptr;
   int* ws_tries_dummy = nullptr;
