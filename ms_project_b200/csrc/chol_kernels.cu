@@ -211,7 +211,9 @@ __device__ __forceinline__ void gemm_body(const Batch& b, int step, const UpdRan
       for (int nt = 0; nt < TG_NT; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
   }
 
-  tile_gemm_nt(acc, A, ld, B, ldb, nchunks, smem, kc_lo, kc_hi);
+  // chunks that can be skipped by some warp: everything for triangular B / diagonal C, the first K tile for triangular A
+  const int n_pred = (tri_b || diag_c) ? nchunks : (tri_a ? NB / TG_KC : 0);
+  tile_gemm_nt(acc, A, ld, B, ldb, nchunks, smem, kc_lo, kc_hi, n_pred);
 
   if (diag_c && kc_hi == 0) return;      // strictly-upper part of a diagonal tile: never read, left untouched
 #pragma unroll

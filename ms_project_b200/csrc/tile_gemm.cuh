@@ -79,9 +79,56 @@ __device__ __forceinline__ void tg_load_stage(double* stage, const double* __res
 // Element (row, col) of the CTA tile held in acc[mt][nt][e]:
 //   row = wm*32 + mt*8 + (lane>>2),  col = wn*32 + nt*8 + (lane&3)*2 + e
 // `load(stage, chunk)` issues the cp.async copies of K-chunk `chunk` (128 A rows, 64 B rows, 16 doubles each) into `stage`.
+// One K-chunk of the skewed pipeline.  PRED = true: the warp's DMMAs are issued only inside [kc_lo, kc_hi); the
+// unpredicated copy exists because the (warp-uniform) test alone costs 3.5 % of the DMMA rate (tools/gemm_probe,
+// "skew+pred": 35.2 vs 36.4 TFLOP/s), so chunks that cannot be skipped run without it.
+template <bool PRED, typename Loader>
+__device__ __forceinline__ void tg_chunk(double (&acc)[TG_MT][TG_NT][2], double (&a)[TG_MT], double (&b)[TG_NT], Loader& load,
+                                         int kc, int nchunks, double* smem, int aoff, int boff, int kc_lo, int kc_hi) {
+  {   // refill the stage chunk kc-1 was read from: every warp passed the barrier of the previous iteration
+    const int nk = kc + TG_STAGES - 1;
+    if (nk < nchunks) load(smem + (nk % TG_STAGES) * TG_STAGE_DOUBLES, nk);
+    cp_async_commit();
+  }
+  const double* As = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + aoff;
+  const double* Bs = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + boff;
+  const double* An = smem + ((kc + 1) % TG_STAGES) * TG_STAGE_DOUBLES + aoff;
+  const double* Bn = smem + ((kc + 1) % TG_STAGES) * TG_STAGE_DOUBLES + boff;
+  const bool act = !PRED || ((kc >= kc_lo) && (kc < kc_hi));   // warp-uniform: otherwise the operands are structurally zero
+#pragma unroll
+  for (int kk = 0; kk < TG_KC; kk += 4) {
+    double a2[TG_MT], b2[TG_NT];
+    if (kk + 4 < TG_KC) {
+#pragma unroll
+      for (int mt = 0; mt < TG_MT; mt++) a2[mt] = As[mt * 8 * TG_LDK + kk + 4];
+#pragma unroll
+      for (int nt = 0; nt < TG_NT; nt++) b2[nt] = Bs[nt * 8 * TG_LDK + kk + 4];
+    } else {
+      cp_async_wait<TG_STAGES - 2>();     // chunk kc+1 has landed (this thread's copies) ...
+      __syncthreads();                    // ... for every thread, and every warp is done reading chunk kc
+#pragma unroll
+      for (int mt = 0; mt < TG_MT; mt++) a2[mt] = An[mt * 8 * TG_LDK];
+#pragma unroll
+      for (int nt = 0; nt < TG_NT; nt++) b2[nt] = Bn[nt * 8 * TG_LDK];
+    }
+    if (act) {
+#pragma unroll
+      for (int mt = 0; mt < TG_MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < TG_NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < TG_MT; mt++) a[mt] = a2[mt];
+#pragma unroll
+    for (int nt = 0; nt < TG_NT; nt++) b[nt] = b2[nt];
+  }
+}
+
+// `load(stage, chunk)` issues the cp.async copies of K-chunk `chunk` (128 A rows, 64 B rows, 16 doubles each) into `stage`.
+// Chunks [0, n_pred) honour the per-warp activity range [kc_lo, kc_hi); chunks from n_pred on are always active.
 template <typename Loader>
 __device__ __forceinline__ void tile_gemm_pipeline(double (&acc)[TG_MT][TG_NT][2], Loader load, int nchunks, double* smem,
-                                                   int kc_lo = 0, int kc_hi = 1 << 30) {
+                                                   int kc_lo = 0, int kc_hi = 1 << 30, int n_pred = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int wm, wn;
   warp_coords(warp, wm, wn);
@@ -102,54 +149,19 @@ __device__ __forceinline__ void tile_gemm_pipeline(double (&acc)[TG_MT][TG_NT][2
 #pragma unroll
   for (int nt = 0; nt < TG_NT; nt++) b[nt] = smem[boff + nt * 8 * TG_LDK];
 
-  for (int kc = 0; kc < nchunks; kc++) {
-    {   // refill the stage chunk kc-1 was read from: every warp passed the barrier of the previous iteration
-      const int nk = kc + TG_STAGES - 1;
-      if (nk < nchunks) load(smem + (nk % TG_STAGES) * TG_STAGE_DOUBLES, nk);
-      cp_async_commit();
-    }
-    const double* As = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + aoff;
-    const double* Bs = smem + (kc % TG_STAGES) * TG_STAGE_DOUBLES + boff;
-    const double* An = smem + ((kc + 1) % TG_STAGES) * TG_STAGE_DOUBLES + aoff;
-    const double* Bn = smem + ((kc + 1) % TG_STAGES) * TG_STAGE_DOUBLES + boff;
-    const bool act = (kc >= kc_lo) && (kc < kc_hi);   // warp-uniform: otherwise the operands are structurally zero
-#pragma unroll
-    for (int kk = 0; kk < TG_KC; kk += 4) {
-      double a2[TG_MT], b2[TG_NT];
-      if (kk + 4 < TG_KC) {
-#pragma unroll
-        for (int mt = 0; mt < TG_MT; mt++) a2[mt] = As[mt * 8 * TG_LDK + kk + 4];
-#pragma unroll
-        for (int nt = 0; nt < TG_NT; nt++) b2[nt] = Bs[nt * 8 * TG_LDK + kk + 4];
-      } else {
-        cp_async_wait<TG_STAGES - 2>();     // chunk kc+1 has landed (this thread's copies) ...
-        __syncthreads();                    // ... for every thread, and every warp is done reading chunk kc
-#pragma unroll
-        for (int mt = 0; mt < TG_MT; mt++) a2[mt] = An[mt * 8 * TG_LDK];
-#pragma unroll
-        for (int nt = 0; nt < TG_NT; nt++) b2[nt] = Bn[nt * 8 * TG_LDK];
-      }
-      if (act) {
-#pragma unroll
-        for (int mt = 0; mt < TG_MT; mt++)
-#pragma unroll
-          for (int nt = 0; nt < TG_NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
-      }
-#pragma unroll
-      for (int mt = 0; mt < TG_MT; mt++) a[mt] = a2[mt];
-#pragma unroll
-      for (int nt = 0; nt < TG_NT; nt++) b[nt] = b2[nt];
-    }
-  }
+  const int np = n_pred < nchunks ? n_pred : nchunks;
+  int kc = 0;
+  for (; kc < np; kc++) tg_chunk<true>(acc, a, b, load, kc, nchunks, smem, aoff, boff, kc_lo, kc_hi);
+  for (; kc < nchunks; kc++) tg_chunk<false>(acc, a, b, load, kc, nchunks, smem, aoff, boff, 0, 0);
   cp_async_wait<0>();
 }
 
 // Contiguous-K form: chunk kc starts at column 16 kc of both operands.
 __device__ __forceinline__ void tile_gemm_nt(double (&acc)[TG_MT][TG_NT][2], const double* __restrict__ A, size_t lda,
                                              const double* __restrict__ B, size_t ldb, int nchunks, double* smem,
-                                             int kc_lo = 0, int kc_hi = 1 << 30) {
+                                             int kc_lo = 0, int kc_hi = 1 << 30, int n_pred = 0) {
   tile_gemm_pipeline(acc, [=](double* stage, int chunk) { tg_load_stage(stage, A, lda, B, ldb, chunk * TG_KC); }, nchunks,
-                     smem, kc_lo, kc_hi);
+                     smem, kc_lo, kc_hi, n_pred);
 }
 
 }  // namespace b200gp

@@ -23,7 +23,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 template <int WM, int WN, int STAGES, int KC, int MINB, int SKEW>
 __global__ void __launch_bounds__(32 * WM * WN, MINB)
-gemm_variant(const double* __restrict__ M, double* __restrict__ Cout, int ld, int K, int tiles_m, int tiles_n) {
+gemm_variant(const double* __restrict__ M, double* __restrict__ Cout, int ld, int K, int tiles_m, int tiles_n, int kc_lo, int kc_hi) {
   constexpr int TM = 32 * WM, TN = 32 * WN, NT = 32 * WM * WN, LDK = KC + 4;
   constexpr int STAGE = (TM + TN) * LDK;
   extern __shared__ __align__(16) double smem[];
@@ -71,7 +71,7 @@ gemm_variant(const double* __restrict__ M, double* __restrict__ Cout, int ld, in
     cp_async_commit();
   }
   const int aoff = (wm * 32 + g) * LDK + tg, boff = TM * LDK + (wn * 32 + g) * LDK + tg;
-  if (SKEW == 0) {
+  if (SKEW == 0) {   // SKEW: 0 barrier at chunk head, 1 skewed, 2 skewed + runtime per-warp activity predicate
     for (int kc = 0; kc < nchunks; kc++) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
@@ -137,10 +137,12 @@ gemm_variant(const double* __restrict__ M, double* __restrict__ Cout, int ld, in
             for (int nt = 0; nt < 4; nt++) b2[nt] = Bn[nt * 8 * LDK];
           }
         }
+        if (SKEW != 2 || (kc >= kc_lo && kc < kc_hi)) {
 #pragma unroll
         for (int mt = 0; mt < 4; mt++)
 #pragma unroll
           for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        }
 #pragma unroll
         for (int mt = 0; mt < 4; mt++) a[mt] = a2[mt];
 #pragma unroll
@@ -175,12 +177,12 @@ void run(const char* name, const double* M, double* C, int ld, int slots, const 
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   for (int K : Ks) {
     dim3 grid((ld / TM) * (ld / TN), slots);
-    fn<<<grid, 32 * WM * WN, smem>>>(M, C, ld, K, ld / TM, ld / TN);
+    fn<<<grid, 32 * WM * WN, smem>>>(M, C, ld, K, ld / TM, ld / TN, 0, 1 << 30);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     const int reps = 3;
     CK(cudaEventRecord(e0));
-    for (int r = 0; r < reps; r++) fn<<<grid, 32 * WM * WN, smem>>>(M, C, ld, K, ld / TM, ld / TN);
+    for (int r = 0; r < reps; r++) fn<<<grid, 32 * WM * WN, smem>>>(M, C, ld, K, ld / TM, ld / TN, 0, 1 << 30);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms = 0;
@@ -215,6 +217,9 @@ int main(int argc, char** argv) {
   CK(cudaDeviceSynchronize());
   std::vector<int> Ks = {128, 512, 2048};
   std::vector<double> chk;
+  run<4, 2, 3, 16, 2, 1>("skew 4x2 S3 KC16 x2", M, C, ld, slots, Ks, &chk);
+  run<4, 2, 3, 16, 2, 2>("skew+pred 4x2 S3 KC16 x2", M, C, ld, slots, Ks, &chk);
+  return 0;
   run<4, 4, 4, 16, 1, 0>("base 4x4 S4 KC16", M, C, ld, slots, Ks, &chk);
   run<4, 4, 4, 16, 1, 1>("skew 4x4 S4 KC16", M, C, ld, slots, Ks, &chk);
   run<4, 4, 3, 16, 1, 0>("base 4x4 S3 KC16", M, C, ld, slots, Ks, &chk);
