@@ -117,6 +117,35 @@ def main():
             if key in d and d[key][0] != '':
                 v, u = d[key]
                 out.append('| %s (`%s`) | %s %s |' % (label, key, v, u))
+        # derived roofline figures: FP64 ALU flops from the SASS op counts, DRAM bandwidth from the byte counters
+        def num(key):
+            try:
+                v, u = d[key]
+                f = float(v.replace(',', ''))
+                scale = {'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12, 'byte': 1.0, 'us': 1e-6, 'ms': 1e-3, 'ns': 1e-9,
+                         's': 1.0, 'usecond': 1e-6, 'msecond': 1e-3, 'nsecond': 1e-9, 'second': 1.0}.get(u, 1.0)
+                return f * scale
+            except Exception:
+                return None
+        t = num('gpu__time_duration.sum')
+        dfma, dmul, dadd = (num('smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed'),
+                            num('smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed'),
+                            num('smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed'))
+        peak_ipc = num('sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained')      # thread-instr / cycle, GPU-wide
+        clk = num('smsp__cycles_elapsed.avg.per_second')
+        rd, wr = num('dram__bytes_read.sum'), num('dram__bytes_write.sum')
+        if t:
+            if None not in (dfma, dmul, dadd, peak_ipc) and (dfma + dmul + dadd) > 0:
+                fl = 2 * dfma + dmul + dadd
+                extra = ''
+                if clk:
+                    extra = ' = %.2f TFLOP/s at %.2f GHz' % (fl * clk / 1e12, clk / 1e9)
+                out.append('| **FP64 ALU throughput** (DFMA / DMUL / DADD thread-instructions per cycle: %.0f / %.0f / %.0f of %.0f issue slots) | '
+                           '%.0f %% of the FP64 issue slots; %.0f flop/cycle%s |'
+                           % (dfma, dmul, dadd, peak_ipc, 100 * (dfma + dmul + dadd) / peak_ipc, fl, extra))
+            if None not in (rd, wr):
+                out.append('| **DRAM bandwidth** (read + write / duration) | %.0f GB/s = %.1f %% of the 6 544 GB/s measured copy peak |'
+                           % ((rd + wr) / t / 1e9, 100 * (rd + wr) / t / 6544e9))
         out.append('')
     open(os.path.join(PROF, 'ncu_%s.md' % tag), 'w').write('\n'.join(out) + '\n')
     print('\n'.join(out[:80]))
