@@ -132,7 +132,12 @@ def main():
                             num('smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed'),
                             num('smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed'))
         peak_ipc = num('sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained')      # thread-instr / cycle, GPU-wide
-        clk = num('smsp__cycles_elapsed.avg.per_second')
+        clk = None
+        try:
+            v, u = d['smsp__cycles_elapsed.avg.per_second']
+            clk = float(v.replace(',', '')) * {'cycle/nsecond': 1e9, 'cycle/usecond': 1e6, 'cycle/second': 1.0, 'Ghz': 1e9, 'Mhz': 1e6, 'hz': 1.0}.get(u, 1e9)
+        except Exception:
+            pass
         rd, wr = num('dram__bytes_read.sum'), num('dram__bytes_write.sum')
         if t:
             if None not in (dfma, dmul, dadd, peak_ipc) and (dfma + dmul + dadd) > 0:
