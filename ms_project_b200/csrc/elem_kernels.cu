@@ -304,6 +304,48 @@ __device__ __forceinline__ void poly_prologue(PolySmem<LMAX>& S, const Batch& b,
   }
 }
 
+// p[e] = product of the leaf values selected by the slot mask `m` (1 for the empty mask).  With 4 slots the 16 masks are a
+// jump table of straight-line products -- exactly the multiplications the term needs; the generic form multiplies through
+// per-bit selects (p *= bit ? v : 1), which cost two FSELs and a wasted DMUL per absent leaf.
+template <int LMAX, int E>
+__device__ __forceinline__ void mask_product(const double (&v)[LMAX][E], unsigned m, double (&p)[E]) {
+  if (LMAX == 4) {
+#define MP1(a) for (int e = 0; e < E; e++) p[e] = v[a][e]; break
+#define MP2(a, b) for (int e = 0; e < E; e++) p[e] = v[a][e] * v[b][e]; break
+#define MP3(a, b, c) for (int e = 0; e < E; e++) p[e] = v[a][e] * v[b][e] * v[c][e]; break
+    switch (m & 15u) {
+      case 0: for (int e = 0; e < E; e++) p[e] = 1.0; break;
+      case 1: MP1(0);
+      case 2: MP1(1);
+      case 4: MP1(2);
+      case 8: MP1(3);
+      case 3: MP2(0, 1);
+      case 5: MP2(0, 2);
+      case 9: MP2(0, 3);
+      case 6: MP2(1, 2);
+      case 10: MP2(1, 3);
+      case 12: MP2(2, 3);
+      case 7: MP3(0, 1, 2);
+      case 11: MP3(0, 1, 3);
+      case 13: MP3(0, 2, 3);
+      case 14: MP3(1, 2, 3);
+      default: for (int e = 0; e < E; e++) p[e] = (v[0][e] * v[1][e]) * (v[2][e] * v[3][e]); break;
+    }
+#undef MP1
+#undef MP2
+#undef MP3
+  } else {
+#pragma unroll
+    for (int e = 0; e < E; e++) p[e] = 1.0;
+#pragma unroll
+    for (int l = 0; l < LMAX; l++)
+      if (m & (1u << l)) {
+#pragma unroll
+        for (int e = 0; e < E; e++) p[e] *= v[l][e];
+      }
+  }
+}
+
 // product-term masks: 4 leaf slots expand to at most 4 terms (one register); 8 slots read shared memory
 template <int LMAX>
 __device__ __forceinline__ unsigned term_mask(unsigned terms4, unsigned term_addr, int g) {
@@ -354,14 +396,7 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_build_kernel(Batc
       for (int g = 0; g < G; g++) {
         const unsigned mask = term_mask<LMAX>(terms4, sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), g);
         double p[E];
-#pragma unroll
-        for (int e = 0; e < E; e++) p[e] = 1.0;
-#pragma unroll
-        for (int l = 0; l < LMAX; l++)
-          if (mask & (1u << l)) {
-#pragma unroll
-            for (int e = 0; e < E; e++) p[e] *= v[l][e];
-          }
+        mask_product<LMAX, E>(v, mask, p);
 #pragma unroll
         for (int e = 0; e < E; e++) k[e] += p[e];
       }
@@ -465,14 +500,7 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_grad_kernel(Batch
               const unsigned mask = term_mask<LMAX>(terms4, sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), t);
               if (!(mask & (1u << l))) continue;
               double p[E];
-#pragma unroll
-              for (int e = 0; e < E; e++) p[e] = 1.0;
-#pragma unroll
-              for (int m = 0; m < LMAX; m++)
-                if (m != l && (mask & (1u << m))) {
-#pragma unroll
-                  for (int e = 0; e < E; e++) p[e] *= v[m][e];
-                }
+              mask_product<LMAX, E>(v, mask & ~(1u << l), p);
 #pragma unroll
               for (int e = 0; e < E; e++) adj[e] += p[e];
             }
