@@ -179,3 +179,48 @@ def test_prior_sample_column_reuse():
     assert np.allclose(h[:, 1], norm.ppf(prob[:, 0], 1.0, 2.0))
     assert np.allclose(h[:, 0], np.exp(norm.ppf(prob[:, 0], 0.0, 1.0)))
     assert np.allclose(h[:, 2], np.exp(norm.ppf(prob[:, 1], 0.5, 0.5)))
+
+
+def test_oracle_lml_and_gradient_match_scikit_learn():
+    """Independent pin of the oracle's exact-inference arithmetic: scikit-learn's GaussianProcessRegressor evaluates the
+    same log marginal likelihood (Rasmussen & Williams alg. 2.1) and its gradient for kernels that coincide with the
+    fork's definitions -- RBF = SE, RationalQuadratic = RQ (alpha = power), ExpSineSquared = PER (exp(-2 sin^2(pi d / p) / l^2),
+    periodic.ipynb#2), sums and products -- with WhiteKernel as the Gaussian noise.  sklearn differentiates w.r.t. log(theta),
+    so its gradient is theta * dLML/dtheta.  (GPy adds 1e-8 to the diagonal, sklearn 1e-10: the noise level absorbs the
+    difference here.)"""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, RationalQuadratic, ExpSineSquared, ConstantKernel as C, WhiteKernel
+    from oracle import gp as ogp, kernels as ok
+    rng = np.random.RandomState(7)
+    X = rng.randn(60, 2)
+    y = np.sin(X[:, :1]) + 0.3 * X[:, 1:] + 0.1 * rng.randn(60, 1)
+    # 1-D leaves act on one column: sklearn kernels are isotropic over all columns, so use the column as the input
+    x0 = X[:, :1]
+    cases = [
+        ('SE_1', [1.7, 0.6], lambda t: C(t[0]) * RBF(t[1])),
+        ('RQ_1', [0.8, 1.3, 0.7], lambda t: C(t[0]) * RationalQuadratic(length_scale=t[1], alpha=t[2])),
+        ('PER_1', [1.2, 2.1, 0.9], lambda t: C(t[0]) * ExpSineSquared(length_scale=t[2], periodicity=t[1])),
+        ('SE_1 + RQ_1', [1.7, 0.6, 0.8, 1.3, 0.7],
+         lambda t: C(t[0]) * RBF(t[1]) + C(t[2]) * RationalQuadratic(length_scale=t[3], alpha=t[4])),
+        ('SE_1 * PER_1', [1.7, 0.6, 1.2, 2.1, 0.9],
+         lambda t: (C(t[0]) * RBF(t[1])) * (C(t[2]) * ExpSineSquared(length_scale=t[4], periodicity=t[3]))),
+    ]
+    noise = 0.05
+    for name, th, make in cases:
+        expr = ok.parse(name)
+        lml, grad, _ = ogp.lml_and_grad(expr, np.array(th), noise, x0, y, dist_mode='direct')
+        kernel = make(th) + WhiteKernel(noise - 1e-10 + 1e-8)
+        gpr = GaussianProcessRegressor(kernel=kernel, alpha=1e-10, optimizer=None).fit(x0, y)
+        ref, ref_g = gpr.log_marginal_likelihood(gpr.kernel_.theta, eval_gradient=True)
+        assert abs(lml - ref) <= 1e-9 * max(1.0, abs(ref)), (name, lml, ref)
+        # map sklearn's log-space gradient (kernel_.theta order) onto the oracle's parameter order by name
+        names = [h.name for h in gpr.kernel_.hyperparameters]
+        vals = np.exp(gpr.kernel_.theta)
+        sk = {}
+        for n_, v_, g_ in zip(names, vals, ref_g):
+            sk.setdefault(round(float(v_), 12), []).append(g_ / v_)
+        got = np.concatenate([grad[:-1], grad[-1:]])
+        want_vals = list(th) + [noise - 1e-10 + 1e-8]
+        for gv, val in zip(got, want_vals):
+            cands = sk[round(float(val), 12)]
+            assert any(abs(gv - c) <= 1e-6 * max(1.0, abs(c)) for c in cands), (name, val, gv, cands)
