@@ -51,7 +51,6 @@ struct b200gp_ctx {
   cudaEvent_t ev[8]{};
   cudaStream_t side = nullptr;     // high-priority stream for the look-ahead panel of large single factorisations
   cudaStream_t peer = nullptr;     // second stream of the two-group batched schedule
-  bool split_groups = true;
   const double* lut = nullptr;     // OP_LOOKUP table (b200gp_set_lookup)
   int lut_n = 0;
   cudaEvent_t evP = nullptr, evR = nullptr, evS = nullptr;
@@ -170,8 +169,7 @@ const char* b200gp_last_error(b200gp_ctx* c) { return c ? c->err.c_str() : "null
 
 int b200gp_set_quirks(b200gp_ctx* c, int mask) {
   if (!c) return -1;
-  c->quirks = mask & 255;
-  c->split_groups = !(mask & 512);     // development switch: bit 9 disables the two-group batched schedule
+  c->quirks = mask & (QUIRK_PER_LENGTHSCALE | QUIRK_LIN_SHIFT);
   return 0;
 }
 
@@ -268,7 +266,7 @@ static void panel_schedule(b200gp_ctx* c, const Batch& b, PanelFn panel, UpdateF
   const bool la = (b.nslots < 8 && T >= 8);
   if (!la) {
     const int W = c->batch_panel_tiles;
-    const bool split = c->split_groups && b.nslots >= 16;
+    const bool split = b.nslots >= 16;
     Batch g[2] = {b, b};
     cudaStream_t st[2] = {c->stream, c->stream};
     int ng = 1;
