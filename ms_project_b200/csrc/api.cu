@@ -88,7 +88,7 @@ struct Carver {
 };
 
 struct Layout {
-  double *M1, *M2, *Dinv, *z, *alpha, *logdet_part, *diag_part, *grad_part, *Xt, *y, *jitter;
+  double *M1, *M2, *Dinv, *z, *alpha, *logdet_part, *diag_part, *grad_part, *solve_part, *Xt, *y, *jitter;
   int *slot_status, *ids, *klist, *kcount;
   CProg* cprog;
   size_t bytes;
@@ -107,6 +107,7 @@ Layout carve(void* ws, int N, int D, int slots, int max_params) {
   l.logdet_part = c.take<double>(S * T);
   l.diag_part = c.take<double>(S * T);
   l.grad_part = c.take<double>(S * tri_count(T) * (size_t)(max_params + 1));
+  l.solve_part = c.take<double>(S * tri_count(T) * (size_t)NB);
   l.Xt = c.take<double>((size_t)D * Np);
   l.y = c.take<double>(Np);
   l.jitter = c.take<double>(S);
@@ -225,7 +226,7 @@ int b200gp_bind(b200gp_ctx* c, void* ws, size_t ws_bytes, int slots, int max_par
   b.N = N; b.Np = round_up(N, NB); b.T = b.Np / NB; b.D = D;
   b.mstride = (size_t)b.Np * b.Np;
   b.M1 = l.M1; b.M2 = l.M2; b.Dinv = l.Dinv; b.z = l.z; b.alpha = l.alpha;
-  b.logdet_part = l.logdet_part; b.diag_part = l.diag_part; b.grad_part = l.grad_part;
+  b.logdet_part = l.logdet_part; b.diag_part = l.diag_part; b.grad_part = l.grad_part; b.solve_part = l.solve_part;
   b.pstride = max_params + 1;
   b.slot_status = l.slot_status;
   b.Xt = l.Xt; b.y = l.y;

@@ -12,7 +12,7 @@
 //   K^-1 (lower):                     (K^-1)_ij = sum_{k>=i} V_ik V_jk^T                            (i>=j)
 #include "kernels.cuh"
 #include "tile_gemm.cuh"
-#include "tile_potrf.cuh"
+#include "tile_potrf_blocked.cuh"
 
 namespace b200gp {
 
@@ -20,25 +20,25 @@ namespace b200gp {
 // Diagonal block: L_kk = chol(A_kk), D_k = L_kk^-1, V_kk = D_k^T, logdet partial, PD status.
 // ------------------------------------------------------------------------------------------------
 constexpr int PD_LDL = NB + 1;
-constexpr int PD_SMEM_BYTES = NB * PD_LDL * 8 + (int)sizeof(TilePotrfSmem) + 64;
+constexpr int PD_SMEM_BYTES = NB * PD_LDL * 8 + (int)sizeof(TileBlockedSmem) + 64;
 
-__global__ void __launch_bounds__(TP_THREADS, 1) potrf_diag_kernel(Batch b, int k) {
+__global__ void __launch_bounds__(TB_THREADS, 1) potrf_diag_kernel(Batch b, int k) {
   const int slot = b.slot0 + blockIdx.x;
   if (b.slot_status[slot] != 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Lsm = reinterpret_cast<double*>(smem_raw);
-  TilePotrfSmem& S = *reinterpret_cast<TilePotrfSmem*>(smem_raw + NB * PD_LDL * 8);
+  TileBlockedSmem& S = *reinterpret_cast<TileBlockedSmem*>(smem_raw + NB * PD_LDL * 8);
 
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   double* A = b.M1 + slot * b.mstride + (size_t)(k * NB) * b.Np + k * NB;
-  double a[TP_R][TP_R];
+  double a[TB_R][TB_R];
 #pragma unroll
-  for (int p = 0; p < TP_R; p++)
+  for (int p = 0; p < TB_R; p++)
 #pragma unroll
-    for (int q = 0; q < TP_R; q++) a[p][q] = A[(size_t)(ty + 16 * p) * b.Np + tx + 16 * q];
+    for (int q = 0; q < TB_R; q++) a[p][q] = A[(size_t)(ty + 16 * p) * b.Np + tx + 16 * q];
 
-  tile_potrf<true>(a, S, NB);
-  if (S.fail != 0) {   // uniform: S.fail was written before the last barrier inside tile_potrf
+  tile_potrf_blocked(a, S);
+  if (S.fail != 0) {   // uniform: S.fail was written before the last barrier inside tile_potrf_blocked
     if (threadIdx.x == 0) b.slot_status[slot] = k * NB + S.fail;
     return;
   }
@@ -53,23 +53,23 @@ __global__ void __launch_bounds__(TP_THREADS, 1) potrf_diag_kernel(Batch b, int 
   }
   // L -> global (lower part of the tile; the strict upper part is zeroed) and -> shared for phase 2
 #pragma unroll
-  for (int p = 0; p < TP_R; p++)
+  for (int p = 0; p < TB_R; p++)
 #pragma unroll
-    for (int q = 0; q < TP_R; q++) {
+    for (int q = 0; q < TB_R; q++) {
       const int i = ty + 16 * p, c = tx + 16 * q;
       const double v = (i >= c) ? a[p][q] : 0.0;
       A[(size_t)i * b.Np + c] = v;
       Lsm[i * PD_LDL + c] = v;
     }
   __syncthreads();
-  tile_trtri(a, Lsm, PD_LDL, S);
+  tile_trtri_blocked(a, Lsm, PD_LDL, S);
   double* Dk = b.Dinv + ((size_t)slot * b.T + k) * (NB * NB);
   __syncthreads();
   // stage D in shared memory so the transposed copy (V_kk = D^T) is written coalesced as well
 #pragma unroll
-  for (int p = 0; p < TP_R; p++)
+  for (int p = 0; p < TB_R; p++)
 #pragma unroll
-    for (int q = 0; q < TP_R; q++) {
+    for (int q = 0; q < TB_R; q++) {
       const int i = ty + 16 * p, c = tx + 16 * q;
       Dk[i * NB + c] = a[p][q];
       Lsm[i * PD_LDL + c] = a[p][q];
@@ -78,16 +78,16 @@ __global__ void __launch_bounds__(TP_THREADS, 1) potrf_diag_kernel(Batch b, int 
   double* V = b.M2 + slot * b.mstride + (size_t)(k * NB) * b.Np + k * NB;
   __syncthreads();
 #pragma unroll
-  for (int p = 0; p < TP_R; p++)
+  for (int p = 0; p < TB_R; p++)
 #pragma unroll
-    for (int q = 0; q < TP_R; q++) {
+    for (int q = 0; q < TB_R; q++) {
       const int i = ty + 16 * p, c = tx + 16 * q;
       V[(size_t)i * b.Np + c] = Lsm[c * PD_LDL + i];
     }
 }
 
 void launch_potrf_diag(const Batch& b, int k, cudaStream_t s) {
-  potrf_diag_kernel<<<b.nslots, TP_THREADS, PD_SMEM_BYTES, s>>>(b, k);
+  potrf_diag_kernel<<<b.nslots, TB_THREADS, PD_SMEM_BYTES, s>>>(b, k);
   g_launch_count++;
 }
 
@@ -294,54 +294,80 @@ void launch_update(const Batch& b, UpdRange r, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------
 // z = V^T y (= L^-1 y),  alpha = V z (= L^-T z)
+//
+// One CTA per 128 x 128 upper tile (j, m), j <= m, of V: a single matrix already fills the GPU (136 CTAs at N = 2048),
+// where a CTA per tile column left 16 CTAs walking 2048 rows each (0.5 of the 3.4 ms a lone evaluation took).  Tile
+// partials go to `solve_part` and are summed in tile order, so the result does not depend on the batch around it.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) zsolve_kernel(Batch b) {
-  const int slot = blockIdx.y, i = blockIdx.x;
+__global__ void __launch_bounds__(256) ztile_kernel(Batch b) {          // part[(m, j)][c] = sum_{r in tile row j} V[r][128 m + c] y[r]
+  const int slot = blockIdx.y;
   if (b.slot_status[slot] != 0) return;
+  int m, j;
+  tri_decode(blockIdx.x, m, j);
   __shared__ double red[256];
+  __shared__ double ys[NB];
   const int c = threadIdx.x & 127, half = threadIdx.x >> 7;
-  const double* V = b.M2 + slot * b.mstride + i * NB + c;
-  const int rows = (i + 1) * NB;
+  if (threadIdx.x < NB) ys[threadIdx.x] = b.y[j * NB + threadIdx.x];
+  __syncthreads();
+  const double* V = b.M2 + slot * b.mstride + (size_t)(j * NB) * b.Np + m * NB + c;
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  int r = half;
-  for (; r + 6 < rows; r += 8) {
-    s0 = fma(V[(size_t)r * b.Np], b.y[r], s0);
-    s1 = fma(V[(size_t)(r + 2) * b.Np], b.y[r + 2], s1);
-    s2 = fma(V[(size_t)(r + 4) * b.Np], b.y[r + 4], s2);
-    s3 = fma(V[(size_t)(r + 6) * b.Np], b.y[r + 6], s3);
+#pragma unroll 4
+  for (int r = half; r < NB; r += 8) {
+    s0 = fma(V[(size_t)r * b.Np], ys[r], s0);
+    s1 = fma(V[(size_t)(r + 2) * b.Np], ys[r + 2], s1);
+    s2 = fma(V[(size_t)(r + 4) * b.Np], ys[r + 4], s2);
+    s3 = fma(V[(size_t)(r + 6) * b.Np], ys[r + 6], s3);
   }
-  for (; r < rows; r += 2) s0 = fma(V[(size_t)r * b.Np], b.y[r], s0);
   red[threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
-  if (half == 0) b.z[(size_t)slot * b.Np + i * NB + c] = red[c] + red[c + 128];
+  if (half == 0) b.solve_part[((size_t)slot * tri_count(b.T) + blockIdx.x) * NB + c] = red[c] + red[c + 128];
 }
 
-__global__ void __launch_bounds__(256) alpha_kernel(Batch b) {
-  const int slot = blockIdx.y, j = blockIdx.x;
+__global__ void __launch_bounds__(NB) zreduce_kernel(Batch b) {         // z[128 m + c] = sum_{j <= m} part[(m, j)][c]
+  const int slot = blockIdx.y, m = blockIdx.x;
   if (b.slot_status[slot] != 0) return;
+  const double* part = b.solve_part + ((size_t)slot * tri_count(b.T) + tri_count(m)) * NB + threadIdx.x;
+  double s = 0.0;
+  for (int j = 0; j <= m; j++) s += part[(size_t)j * NB];
+  b.z[(size_t)slot * b.Np + m * NB + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) atile_kernel(Batch b) {          // part[(m, j)][r] = sum_c V[128 j + r][128 m + c] z[128 m + c]
+  const int slot = blockIdx.y;
+  if (b.slot_status[slot] != 0) return;
+  int m, j;
+  tri_decode(blockIdx.x, m, j);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const double* z = b.z + (size_t)slot * b.Np;
+  const double* z = b.z + (size_t)slot * b.Np + m * NB + lane * 4;
+  const double4 zz = *reinterpret_cast<const double4*>(z);
+  const double* V = b.M2 + slot * b.mstride + (size_t)(j * NB) * b.Np + m * NB + lane * 4;
+  double* part = b.solve_part + ((size_t)slot * tri_count(b.T) + blockIdx.x) * NB;
+#pragma unroll 4
   for (int rr = warp; rr < NB; rr += 8) {
-    const int r = j * NB + rr;
-    const double* Vr = b.M2 + slot * b.mstride + (size_t)r * b.Np;
-    double s = 0.0;
-    for (int c = j * NB + lane * 2; c < b.Np; c += 64) {
-      const double2 v = *reinterpret_cast<const double2*>(Vr + c);
-      const double2 zz = *reinterpret_cast<const double2*>(z + c);
-      s = fma(v.x, zz.x, s);
-      s = fma(v.y, zz.y, s);
-    }
+    const double4 v = *reinterpret_cast<const double4*>(V + (size_t)rr * b.Np);
+    double s = fma(v.x, zz.x, fma(v.y, zz.y, fma(v.z, zz.z, v.w * zz.w)));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) b.alpha[(size_t)slot * b.Np + r] = s;
+    if (lane == 0) part[rr] = s;
   }
+}
+
+__global__ void __launch_bounds__(NB) areduce_kernel(Batch b) {         // alpha[128 j + r] = sum_{m >= j} part[(m, j)][r]
+  const int slot = blockIdx.y, j = blockIdx.x;
+  if (b.slot_status[slot] != 0) return;
+  const double* part = b.solve_part + (size_t)slot * tri_count(b.T) * NB + threadIdx.x;
+  double s = 0.0;
+  for (int m = j; m < b.T; m++) s += part[(size_t)(tri_count(m) + j) * NB];
+  b.alpha[(size_t)slot * b.Np + j * NB + threadIdx.x] = s;
 }
 
 void launch_solve(const Batch& b, cudaStream_t s) {
-  dim3 grid(b.T, b.nslots);
-  zsolve_kernel<<<grid, 256, 0, s>>>(b);
-  alpha_kernel<<<grid, 256, 0, s>>>(b);
-  g_launch_count += 2;
+  dim3 tiles(tri_count(b.T), b.nslots), cols(b.T, b.nslots);
+  ztile_kernel<<<tiles, 256, 0, s>>>(b);
+  zreduce_kernel<<<cols, NB, 0, s>>>(b);
+  atile_kernel<<<tiles, 256, 0, s>>>(b);
+  areduce_kernel<<<cols, NB, 0, s>>>(b);
+  g_launch_count += 4;
 }
 
 int configure_chol_kernels() {

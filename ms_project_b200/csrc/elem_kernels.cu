@@ -735,11 +735,18 @@ __global__ void __launch_bounds__(256) finalize_kernel(Batch b, int with_grad) {
   if (with_grad) {
     const int ntiles = tri_count(b.T);
     const double* gp = b.grad_part + (size_t)slot * ntiles * b.pstride;
-    for (int p = threadIdx.x; p <= np; p += blockDim.x) {
+    // one warp per parameter: lane l sums tiles l, l + 32, ... in order, then a fixed shuffle tree (the order never
+    // depends on the batch around this item)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int p = warp; p <= np; p += 8) {
       double g = 0.0;
-      for (int t = 0; t < ntiles; t++) g += gp[(size_t)t * b.pstride + p];
-      b.dlml[th0 + p] = g;
-      if (!(fabs(g) < 1.7e308)) bad = 1;
+      for (int t = lane; t < ntiles; t += 32) g += gp[(size_t)t * b.pstride + p];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+      if (lane == 0) {
+        b.dlml[th0 + p] = g;
+        if (!(fabs(g) < 1.7e308)) bad = 1;
+      }
     }
   }
   __syncthreads();

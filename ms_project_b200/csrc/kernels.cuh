@@ -22,6 +22,7 @@ struct Batch {
   double* logdet_part;       // [slot][T]
   double* diag_part;         // [slot][T]   partial sums of diag(K_y) (jitter ladder)
   double* grad_part;         // [slot][ntiles][pstride]
+  double* solve_part;        // [slot][ntiles][NB] tile partials of z = V^T y, then of alpha = V z
   int pstride;
   int* slot_status;          // [slot] 0 ok, >0 = 1-based index of first bad pivot
   // shared data
