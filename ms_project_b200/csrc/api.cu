@@ -1,6 +1,7 @@
 // C-ABI of libb200gp (include/b200gp.h): context, workspace carving, phase orchestration, jitter ladder.
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -38,7 +39,9 @@ struct b200gp_ctx {
   Batch base{};             // geometry + workspace pointers
   int slots = 0, max_params = 0;
   int panel_tiles = 4;          // look-ahead Cholesky (single large matrix)
+  bool panel_user = false;      // b200gp_set_panel_tiles was called: no adaptive choice
   int batch_panel_tiles = 8;    // batched Cholesky / L^-T (measured: 4 -> 26.6, 8 -> 26.2 ms per 256 items at N = 2048)
+  int la_slots = 65;            // batches below this many slots take the look-ahead / pipelined (latency) schedules
   double* ws_jitter = nullptr;
   int* ws_ids = nullptr;
   int* ws_tries_dummy = nullptr;
@@ -53,7 +56,8 @@ struct b200gp_ctx {
   cudaStream_t peer = nullptr;     // second stream of the two-group batched schedule
   const double* lut = nullptr;     // OP_LOOKUP table (b200gp_set_lookup)
   int lut_n = 0;
-  cudaEvent_t evP = nullptr, evR = nullptr, evS = nullptr;
+  cudaEvent_t evP = nullptr, evR = nullptr, evS = nullptr, evI = nullptr;
+  std::vector<cudaEvent_t> evC;    // Cholesky panel p finished (small batches: the L^-T phase follows panel by panel)
   float phase_ms[6]{};
   int n_phase = 0;
 };
@@ -147,6 +151,8 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
   cudaEventCreateWithFlags(&c->evP, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->evR, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->evS, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->evI, cudaEventDisableTiming);
+  if (const char* e = getenv("B200GP_LA_SLOTS")) { const int v = atoi(e); if (v >= 0 && v <= 4096) c->la_slots = v; }   // tuning aid
   *out = c;
   return 0;
 }
@@ -157,7 +163,8 @@ int b200gp_destroy(b200gp_ctx* c) {
   for (auto& e : c->ev) cudaEventDestroy(e);
   if (c->side) cudaStreamDestroy(c->side);
   if (c->peer) cudaStreamDestroy(c->peer);
-  if (c->evP) { cudaEventDestroy(c->evP); cudaEventDestroy(c->evR); cudaEventDestroy(c->evS); }
+  if (c->evP) { cudaEventDestroy(c->evP); cudaEventDestroy(c->evR); cudaEventDestroy(c->evS); cudaEventDestroy(c->evI); }
+  for (auto& e : c->evC) cudaEventDestroy(e);
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->h_ids) cudaFreeHost(c->h_ids);
   if (c->h_diag) cudaFreeHost(c->h_diag);
@@ -186,6 +193,7 @@ int b200gp_set_panel_tiles(b200gp_ctx* c, int tiles) {
   if (!c || tiles < 1 || tiles > 16) return -1;
   c->panel_tiles = tiles;
   c->batch_panel_tiles = tiles;
+  c->panel_user = true;
   return 0;
 }
 
@@ -261,10 +269,20 @@ int b200gp_bind(b200gp_ctx* c, void* ws, size_t ws_bytes, int slots, int max_par
 //  * few slots (a single large matrix): look-ahead.  The next panel (its priority update, the latency-bound diagonal
 //    factorisations and the TRSMs) runs on a high-priority side stream while the main stream is still applying the
 //    current panel to the rest of the trailing matrix, so the panel disappears behind the DMMA update.
+// Panel width of the look-ahead schedule.  Large single matrices (T > 32) want wide panels (trailing update with
+// K = 512: C tiles are re-read 4x less often).  Small batches of moderate order are latency-bound -- the chain
+// potrf -> trsm -> update of the next column is the evaluation time -- and want the shortest chain: one tile column per
+// panel, so the update in front of every diagonal factorisation has K = 128 (measured at N = 2048: 1 item 2.2 -> 1.9 ms,
+// 8 items 4.1 -> 3.5 ms with W = 1; from ~16 items on W = 2 is as good or better).
+static int la_panel_width(const b200gp_ctx* c, const Batch& b) {
+  if (c->panel_user || b.T > 32) return c->panel_tiles;
+  return b.nslots <= 12 ? 1 : 2;
+}
+
 template <typename PanelFn, typename UpdateFn>
 static void panel_schedule(b200gp_ctx* c, const Batch& b, PanelFn panel, UpdateFn update) {
   const int T = b.T;
-  const bool la = (b.nslots < 8 && T >= 8);
+  const bool la = (b.nslots < c->la_slots && T >= 8);
   if (!la) {
     const int W = c->batch_panel_tiles;
     const bool split = b.nslots >= 16;
@@ -295,7 +313,7 @@ static void panel_schedule(b200gp_ctx* c, const Batch& b, PanelFn panel, UpdateF
     return;
   }
   cudaStream_t s0 = c->stream, s1 = c->side;
-  const int W = c->panel_tiles;
+  const int W = la_panel_width(c, b);
   cudaEventRecord(c->evS, s0);
   cudaStreamWaitEvent(s1, c->evS, 0);
   panel(b, 0, W < T ? W : T, s1);
@@ -316,8 +334,10 @@ static void panel_schedule(b200gp_ctx* c, const Batch& b, PanelFn panel, UpdateF
   cudaStreamWaitEvent(s0, c->evP, 0);
 }
 
-// Right-looking blocked Cholesky of every slot of `b` (M1 in place).
-static void cholesky_phase(b200gp_ctx* c, const Batch& b) {
+// Right-looking blocked Cholesky of every slot of `b` (M1 in place).  `panel_done(k0, stream)`, if given, is called when
+// the tile columns of the panel starting at k0 are final.
+template <typename DoneFn>
+static void cholesky_phase_impl(b200gp_ctx* c, const Batch& b, DoneFn panel_done) {
   const int T = b.T;
   panel_schedule(
       c, b,
@@ -327,22 +347,54 @@ static void cholesky_phase(b200gp_ctx* c, const Batch& b) {
           launch_potrf_diag(g, k, s);
           if (k + 1 < T) launch_gemm(g, GM_TRSM, k, s);
         }
+        panel_done(k0, s);
       },
       [&](const Batch& g, int k0, int W, int j0, int j1, cudaStream_t s) { launch_update(g, UpdRange{k0, W, j0, j1}, s); });
 }
 
-// Right-looking V = L^-T (upper tiles of M2): column i is finished by V_ji = -S_ji D_i^T (j < i), then pushes its
-// contribution S_jm += V_ji L_mi^T to every column m > i.
+static void cholesky_phase(b200gp_ctx* c, const Batch& b) {
+  cholesky_phase_impl(c, b, [](int, cudaStream_t) {});
+}
+
+// One panel of the right-looking V = L^-T (upper tiles of M2): column i is finished by V_ji = -S_ji D_i^T (j < i), then
+// pushes its contribution S_jm += V_ji L_mi^T to every column m > i.
+static void inverse_panel(const Batch& g, int k0, int k1, cudaStream_t s) {
+  for (int i = k0; i < k1; i++) {      // left-looking inside the panel, like the Cholesky
+    if (i > k0) launch_vupdate(g, UpdRange{k0, i - k0, i, i + 1}, s);
+    if (i > 0) launch_gemm(g, GM_VTRSM, i, s);
+  }
+}
+
 static void inverse_phase(b200gp_ctx* c, const Batch& b) {
   panel_schedule(
-      c, b,
-      [&](const Batch& g, int k0, int k1, cudaStream_t s) {
-        for (int i = k0; i < k1; i++) {      // left-looking inside the panel, like the Cholesky
-          if (i > k0) launch_vupdate(g, UpdRange{k0, i - k0, i, i + 1}, s);
-          if (i > 0) launch_gemm(g, GM_VTRSM, i, s);
-        }
-      },
+      c, b, [&](const Batch& g, int k0, int k1, cudaStream_t s) { inverse_panel(g, k0, k1, s); },
       [&](const Batch& g, int k0, int W, int j0, int j1, cudaStream_t s) { launch_vupdate(g, UpdRange{k0, W, j0, j1}, s); });
+}
+
+// Few slots of moderate order (the tail of a lock-step fit: a handful of items at N ~ 2048): every launch is a few CTAs
+// on 148 SMs and the evaluation time is the length of the dependency chain, not the flops.  Panel p of L^-T only needs
+// panel p of L, so it runs on a third stream as soon as the Cholesky has finished that panel, hidden behind the (longer)
+// chain of the next Cholesky panel.
+static bool pipelined_inverse(const b200gp_ctx* c, const Batch& b) { return b.nslots < c->la_slots && b.T >= 8 && b.T <= 32; }
+
+static void cholesky_inverse_pipelined(b200gp_ctx* c, const Batch& b) {
+  const int T = b.T, W = la_panel_width(c, b);
+  const int npanels = (T + W - 1) / W;
+  while ((int)c->evC.size() < npanels) {
+    cudaEvent_t e;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    c->evC.push_back(e);
+  }
+  cholesky_phase_impl(c, b, [&](int k0, cudaStream_t s) { cudaEventRecord(c->evC[k0 / W], s); });
+  cudaStream_t s2 = c->peer;
+  for (int p = 0; p < npanels; p++) {
+    const int k0 = p * W, k1 = (k0 + W < T) ? k0 + W : T;
+    cudaStreamWaitEvent(s2, c->evC[p], 0);
+    inverse_panel(b, k0, k1, s2);
+    if (k1 < T) launch_vupdate(b, UpdRange{k0, k1 - k0, k1, T}, s2);
+  }
+  cudaEventRecord(c->evI, s2);
+  cudaStreamWaitEvent(c->stream, c->evI, 0);
 }
 
 static int lml_grad_impl(b200gp_ctx* c, const int32_t* prog, const int32_t* prog_off, const double* theta,
@@ -358,9 +410,14 @@ static void run_pipeline(b200gp_ctx* c, const Batch& b, int with_grad) {
   launch_compile(b, s);
   launch_build_k(b, s);
   if (prof) cudaEventRecord(c->ev[1], s);
-  cholesky_phase(c, b);
-  if (prof) cudaEventRecord(c->ev[2], s);
-  inverse_phase(c, b);
+  if (pipelined_inverse(c, b)) {
+    cholesky_inverse_pipelined(c, b);       // the "cholesky" phase time then covers both, "inverse" reads 0
+    if (prof) cudaEventRecord(c->ev[2], s);
+  } else {
+    cholesky_phase(c, b);
+    if (prof) cudaEventRecord(c->ev[2], s);
+    inverse_phase(c, b);
+  }
   if (prof) cudaEventRecord(c->ev[3], s);
   launch_solve(b, s);
   if (prof) cudaEventRecord(c->ev[4], s);

@@ -228,14 +228,21 @@ __device__ __forceinline__ void gemm_body(const Batch& b, int step, const UpdRan
 }
 
 // One named kernel per blocked step, so launch lists and ncu captures tell the phases apart.
-__global__ void __launch_bounds__(TG_THREADS, 2) chol_trsm_kernel(Batch b, int step, int hf) {
-  gemm_body<GM_TRSM>(b, step, UpdRange{0, 0, 0, 0}, blockIdx.x, hf);
+// In-place triangular solves: the right half of a tile reads all 128 columns and writes columns 64..127, the left half
+// reads and writes columns 0..63 only -- so ONE CTA does the right half first, then the left half (two launches with
+// sibling CTAs before: 2 x 11 us on the critical path of every tile column of a small batch).
+__global__ void __launch_bounds__(TG_THREADS, 2) chol_trsm_kernel(Batch b, int step) {
+  gemm_body<GM_TRSM>(b, step, UpdRange{0, 0, 0, 0}, blockIdx.x, 1);
+  __syncthreads();
+  gemm_body<GM_TRSM>(b, step, UpdRange{0, 0, 0, 0}, blockIdx.x, 0);
 }
 __global__ void __launch_bounds__(TG_THREADS, 2) chol_update_kernel(Batch b, UpdRange r) {
   gemm_body<GM_UPD>(b, r.k0, r, blockIdx.x >> 1, blockIdx.x & 1);
 }
-__global__ void __launch_bounds__(TG_THREADS, 2) inv_trsm_kernel(Batch b, int step, int hf) {
-  gemm_body<GM_VTRSM>(b, step, UpdRange{0, 0, 0, 0}, blockIdx.x, hf);
+__global__ void __launch_bounds__(TG_THREADS, 2) inv_trsm_kernel(Batch b, int step) {
+  gemm_body<GM_VTRSM>(b, step, UpdRange{0, 0, 0, 0}, blockIdx.x, 1);
+  __syncthreads();
+  gemm_body<GM_VTRSM>(b, step, UpdRange{0, 0, 0, 0}, blockIdx.x, 0);
 }
 __global__ void __launch_bounds__(TG_THREADS, 2) inv_update_kernel(Batch b, UpdRange r) {
   gemm_body<GM_VUPD>(b, r.k0, r, blockIdx.x >> 1, blockIdx.x & 1);
@@ -254,17 +261,11 @@ void launch_gemm(const Batch& b, int mode, int step, cudaStream_t s) {
   if (ntiles <= 0) return;
   dim3 grid(ntiles, b.nslots);
   switch (mode) {
-    // In-place triangular solves: the right half reads all 128 columns of the tile and writes columns 64..127, the
-    // left half reads and writes columns 0..63 only -- so the right halves go first, the left halves in a second launch.
     case GM_TRSM:
-      chol_trsm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, step, 1);
-      chol_trsm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, step, 0);
-      g_launch_count++;
+      chol_trsm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, step);
       break;
     case GM_VTRSM:
-      inv_trsm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, step, 1);
-      inv_trsm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, step, 0);
-      g_launch_count++;
+      inv_trsm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, step);
       break;
     default:
       grid.x *= 2;

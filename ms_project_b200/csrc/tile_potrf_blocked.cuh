@@ -168,11 +168,15 @@ __device__ __forceinline__ void tb_panel_solve(TileBlockedSmem& S, double* pan, 
   }
 }
 
+#ifdef TB_EXPERIMENT_SMALL_CODE      // tools/potrf_probe.cu only: one case for every step (wrong numerics, timing of the code-size effect)
+#define TB_DISPATCH(jb, CALL) CALL(0);
+#else
 #define TB_DISPATCH(jb, CALL)                                                                     \
   switch (jb) {                                                                                   \
     case 0: CALL(0); break; case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; \
     case 4: CALL(4); break; case 5: CALL(5); break; case 6: CALL(6); break; default: CALL(7); break; \
   }
+#endif
 
 // Phase 1.  a[p][q] = element (ty + 16 p, tx + 16 q) of the tile (lower part valid on entry).  On exit a holds L
 // (blocks p >= q; exact zeros above the diagonal inside the diagonal blocks, blocks p < q untouched), S.T the inverses

@@ -45,7 +45,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) probe(double* A, double* Dout, 
     }
   __syncthreads();
   long long t3 = clock64();
+#ifndef TB_EXPERIMENT_SMALL_CODE
   tile_trtri_blocked(a, Lsm, LDL, S);
+#endif
   __syncthreads();
   long long t4 = clock64();
 #pragma unroll
