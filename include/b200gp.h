@@ -144,8 +144,12 @@ int b200gp_vector_pairs(b200gp_ctx* ctx, const double* d_G, int M, int S, int n,
  * stream: [build_K, cholesky, inverse(V), solve, Kinv, grad+finalize].  Returns the number written. */
 int b200gp_last_phase_ms(b200gp_ctx* ctx, float* out, int cap);
 int b200gp_set_profiling(b200gp_ctx* ctx, int enabled);
-/* panel width (in 128-column tiles) of the look-ahead Cholesky used for single large matrices; default 2 */
+/* panel width (in 128-column tiles) of the blocked Cholesky / L^-T schedules; the default is chosen per batch
+ * (1-2 tile columns for latency-bound small batches, 4 for a single large matrix, 8 for large batches) */
 int b200gp_set_panel_tiles(b200gp_ctx* ctx, int tiles);
+/* 1: K^-1 and the gradient pass of the <= 4-leaf programs run as ONE kernel (K^-1 never reaches HBM); 0 (default): two
+ * kernels.  Same results up to the order of the partial sums; measured +0.8 % throughput at N = 2048. */
+int b200gp_set_fused_grad(b200gp_ctx* ctx, int enabled);
 /* kernels launched by this context since creation (for bench.py's gpu_launches) */
 long long b200gp_launch_count(b200gp_ctx* ctx);
 

@@ -41,6 +41,7 @@ struct b200gp_ctx {
   int panel_tiles = 4;          // look-ahead Cholesky (single large matrix)
   bool panel_user = false;      // b200gp_set_panel_tiles was called: no adaptive choice
   int batch_panel_tiles = 8;    // batched Cholesky / L^-T (measured: 4 -> 26.6, 8 -> 26.2 ms per 256 items at N = 2048)
+  bool fused_grad = false;      // K^-1 and the gradient of the <= 4-leaf programs in one kernel (kinv_grad_kernel)
   int la_slots = 65;            // batches below this many slots take the look-ahead / pipelined (latency) schedules
   double* ws_jitter = nullptr;
   int* ws_ids = nullptr;
@@ -110,7 +111,7 @@ Layout carve(void* ws, int N, int D, int slots, int max_params) {
   l.alpha = c.take<double>(S * Np);
   l.logdet_part = c.take<double>(S * T);
   l.diag_part = c.take<double>(S * T);
-  l.grad_part = c.take<double>(S * tri_count(T) * (size_t)(max_params + 1));
+  l.grad_part = c.take<double>(S * tri_count(T) * 2 * (size_t)(max_params + 1));
   l.solve_part = c.take<double>(S * tri_count(T) * (size_t)NB);
   l.Xt = c.take<double>((size_t)D * Np);
   l.y = c.take<double>(Np);
@@ -152,6 +153,7 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
   cudaEventCreateWithFlags(&c->evR, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->evS, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->evI, cudaEventDisableTiming);
+  if (const char* e = getenv("B200GP_FUSED_GRAD")) c->fused_grad = atoi(e) != 0;                                          // tuning aid
   if (const char* e = getenv("B200GP_LA_SLOTS")) { const int v = atoi(e); if (v >= 0 && v <= 4096) c->la_slots = v; }   // tuning aid
   *out = c;
   return 0;
@@ -194,6 +196,12 @@ int b200gp_set_panel_tiles(b200gp_ctx* c, int tiles) {
   c->panel_tiles = tiles;
   c->batch_panel_tiles = tiles;
   c->panel_user = true;
+  return 0;
+}
+
+int b200gp_set_fused_grad(b200gp_ctx* c, int enabled) {
+  if (!c) return -1;
+  c->fused_grad = enabled != 0;
   return 0;
 }
 
@@ -421,9 +429,11 @@ static void run_pipeline(b200gp_ctx* c, const Batch& b, int with_grad) {
   if (prof) cudaEventRecord(c->ev[3], s);
   launch_solve(b, s);
   if (prof) cudaEventRecord(c->ev[4], s);
-  if (with_grad) launch_gemm(b, GM_KINV, 0, s);
+  if (with_grad) {
+    if (c->fused_grad) launch_kinv_grad(b, s); else launch_gemm(b, GM_KINV, 0, s);
+  }
   if (prof) cudaEventRecord(c->ev[5], s);
-  if (with_grad) launch_grad(b, s);
+  if (with_grad) launch_grad(b, s, c->fused_grad);
   launch_finalize(b, with_grad, s);
   if (prof) cudaEventRecord(c->ev[6], s);
 }

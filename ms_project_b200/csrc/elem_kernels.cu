@@ -12,10 +12,19 @@
 // All of them are persistent (grid = resident CTAs, grid-stride over (slot, tile) work items), so an empty list
 // costs one wave of CTAs that exit at once.
 #include "kernels.cuh"
+#include "gemm_body.cuh"
 #include "kprog.cuh"
 #include "cprog.cuh"
 #include "fastmath.cuh"
 #include <cstddef>
+
+// rows a thread of the polynomial-form kernels interleaves (independent FP64 chains)
+#ifndef POLY_E4
+#define POLY_E4 2
+#endif
+#ifndef POLY_E8
+#define POLY_E8 1
+#endif
 
 namespace b200gp {
 
@@ -269,7 +278,7 @@ __device__ __forceinline__ double leaf_grad_scale(int op, const double* cst, dou
 // Cooperative prologue of one (slot, tile) work item: program, leaf constants, row-side tables; returns the
 // column-side values of this thread's column and the leaf opcodes in registers.
 template <int LMAX>
-__device__ __forceinline__ void poly_prologue(PolySmem<LMAX>& S, const Batch& b, int slot, int ti, int tj,
+__device__ __forceinline__ void poly_prologue(PolySmem<LMAX>& S, const Batch& b, int slot, int ti, int tj, int colc,
                                               double (&Aj)[LMAX], double (&Sj)[LMAX], double (&Cj)[LMAX], int (&ops)[LMAX]) {
   __syncthreads();                                           // the previous work item is done with S
   if (threadIdx.x < (int)(sizeof(CProg) / 4))
@@ -281,15 +290,15 @@ __device__ __forceinline__ void poly_prologue(PolySmem<LMAX>& S, const Batch& b,
   if (threadIdx.x < L) leaf_constants(S.cp.leaf[threadIdx.x].x, b.theta + th0 + S.cp.leaf[threadIdx.x].z, S.cst[threadIdx.x], S.ivar[threadIdx.x]);
   if (threadIdx.x == 32) S.noise = b.theta[b.theta_off[item + 1] - 1];
   __syncthreads();
-  const int c = threadIdx.x & (NB - 1);
-  if (threadIdx.x < NB) {
+  if (threadIdx.x < NB) {        // row-side tables of the 128 rows of tile row ti
+    const int r = threadIdx.x;
 #pragma unroll
     for (int l = 0; l < LMAX; l++)
       if (l < L) {
         const int4 lf = S.cp.leaf[l];
         double A, Sv, Cv;
-        point_values(lf.x, S.cst[l], b.Xt[(size_t)lf.y * b.Np + ti * NB + c], A, Sv, Cv);
-        S.Ai[l][c] = A; S.Si[l][c] = Sv; S.Ci[l][c] = Cv;
+        point_values(lf.x, S.cst[l], b.Xt[(size_t)lf.y * b.Np + ti * NB + r], A, Sv, Cv);
+        S.Ai[l][r] = A; S.Si[l][r] = Sv; S.Ci[l][r] = Cv;
       }
   }
 #pragma unroll
@@ -299,7 +308,7 @@ __device__ __forceinline__ void poly_prologue(PolySmem<LMAX>& S, const Batch& b,
     if (l < L) {
       const int4 lf = S.cp.leaf[l];
       ops[l] = lf.x;
-      point_values(lf.x, S.cst[l], b.Xt[(size_t)lf.y * b.Np + tj * NB + c], Aj[l], Sj[l], Cj[l]);
+      point_values(lf.x, S.cst[l], b.Xt[(size_t)lf.y * b.Np + tj * NB + colc], Aj[l], Sj[l], Cj[l]);   // this thread's column
     }
   }
 }
@@ -372,7 +381,7 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_build_kernel(Batc
     tri_decode((int)(w % ntiles), ti, tj);
     double Aj[LMAX], Sj[LMAX], Cj[LMAX];
     int ops[LMAX];
-    poly_prologue<LMAX>(S, b, slot, ti, tj, Aj, Sj, Cj, ops);
+    poly_prologue<LMAX>(S, b, slot, ti, tj, c, Aj, Sj, Cj, ops);
     __syncthreads();
     const int L = S.cp.L, G = S.cp.G;
     const unsigned terms4 = *reinterpret_cast<const unsigned*>(S.cp.term);
@@ -421,121 +430,186 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_build_kernel(Batc
   }
 }
 
+// Gradient contribution of the COLS columns [col0, col0 + COLS) of tile (ti, tj).  Thread (c, h) = (tid % COLS, tid / COLS)
+// owns column col0 + c and the rows [h RPH, (h + 1) RPH), RPH = 128 COLS / 256.  `Kt` points at (row 0, column col0) of the
+// K^-1 tile, `kld` is its row stride: global memory (Np) for the stand-alone kernel, the staged copy in shared memory for
+// the fused K^-1 + gradient kernel.  `out`: this work item's entry of grad_part.
+template <int LMAX, int E, int COLS>
+__device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, const Batch& b, int slot, int ti, int tj, int col0,
+                                               const double* Kt, size_t kld, double* out) {
+  typedef PolySmem<LMAX> SM;
+  constexpr int NV = 3 * LMAX + 1;
+  constexpr int RPH = NB * COLS / 256;
+  const int c = threadIdx.x % COLS, h = threadIdx.x / COLS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double Aj[LMAX], Sj[LMAX], Cj[LMAX];
+  int ops[LMAX];
+  poly_prologue<LMAX>(S, b, slot, ti, tj, col0 + c, Aj, Sj, Cj, ops);
+  if (threadIdx.x >= NB) S.ai[threadIdx.x - NB] = b.alpha[(size_t)slot * b.Np + ti * NB + threadIdx.x - NB];
+  const double aj = b.alpha[(size_t)slot * b.Np + tj * NB + col0 + c];
+  __syncthreads();
+  const int L = S.cp.L, G = S.cp.G, single = S.cp.single;
+  const unsigned terms4 = *reinterpret_cast<const unsigned*>(S.cp.term);
+  double acc[LMAX][3], accn = 0.0;
+#pragma unroll
+  for (int l = 0; l < LMAX; l++) { acc[l][0] = 0.0; acc[l][1] = 0.0; acc[l][2] = 0.0; }
+  const double* Kinv = Kt + c;
+  const int gj = tj * NB + col0 + c;
+  // diagonal tiles: rows above this warp's first column hold no lower-triangle element
+  int rbeg = h * RPH;
+  if (ti == tj) { const int cmin = col0 + c - lane; if (cmin > rbeg) rbeg = cmin / E * E; }
+  const int rend = h * RPH + RPH;
+  double kv[E];
+#pragma unroll
+  for (int e = 0; e < E; e++) kv[e] = (rbeg < rend) ? Kinv[(size_t)(rbeg + e) * kld] : 0.0;
+#pragma unroll 1
+  for (int r0 = rbeg; r0 < rend; r0 += E) {
+    double wt[E], ar[E];
+    lds_rows<E>(sb + (unsigned)offsetof(SM, ai) + r0 * 8, ar);
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      const int gi = ti * NB + r0 + e;
+      double wv = 0.5 * (ar[e] * aj - kv[e]);
+      const bool valid = gi < b.N && gj <= gi;       // gj <= gi < N
+      if (gi == gj) { if (valid) accn += wv; } else wv *= 2.0;      // symmetric pair (i, j), (j, i)
+      wt[e] = valid ? wv : 0.0;
+    }
+    if (r0 + E < rend) {
+#pragma unroll
+      for (int e = 0; e < E; e++) kv[e] = Kinv[(size_t)(r0 + E + e) * kld];
+    }
+    double v[LMAX][E], aux[LMAX][E];
+#pragma unroll
+    for (int l = 0; l < LMAX; l++)
+      if (l < L) {
+        double Ar[E];
+        lds_rows<E>(sb + (unsigned)offsetof(SM, Ai) + (l * NB + r0) * 8, Ar);
+        leaf_fwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, Ar, sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8,
+                    sb + (unsigned)offsetof(SM, Ci) + (l * NB + r0) * 8, Aj[l], Sj[l], Cj[l], v[l], aux[l]);
+      }
+#pragma unroll
+    for (int l = 0; l < LMAX; l++)
+      if (l < L) {
+        double g[E];
+        if (single) {
+#pragma unroll
+          for (int e = 0; e < E; e++) g[e] = wt[e];
+        } else {
+          double adj[E];
+#pragma unroll
+          for (int e = 0; e < E; e++) adj[e] = 0.0;
+          for (int t = 0; t < G; t++) {
+            const unsigned mask = term_mask<LMAX>(terms4, sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), t);
+            if (!(mask & (1u << l))) continue;
+            double p[E];
+            mask_product<LMAX, E>(v, mask & ~(1u << l), p);
+#pragma unroll
+            for (int e = 0; e < E; e++) adj[e] += p[e];
+          }
+#pragma unroll
+          for (int e = 0; e < E; e++) g[e] = wt[e] * adj[e];
+        }
+        double Ar[E];
+        lds_rows<E>(sb + (unsigned)offsetof(SM, Ai) + (l * NB + r0) * 8, Ar);
+        leaf_bwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, Ar, sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8,
+                    sb + (unsigned)offsetof(SM, Ci) + (l * NB + r0) * 8, Aj[l], Sj[l], Cj[l], g, v[l], aux[l], acc[l]);
+      }
+  }
+  // CTA reduction in a fixed order: lanes (shuffle tree), then the 8 warps
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    double x = (i == NV - 1) ? accn : acc[i / 3][i % 3];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) S.red[warp][i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    const int i = threadIdx.x;
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) s += S.red[q][i];
+    if (i == NV - 1) out[S.cp.nparam] = s;
+    else {
+      const int l = i / 3, p = i % 3;
+      if (l < L && p < S.cp.leaf[l].w)
+        out[S.cp.leaf[l].z + p] = s * leaf_grad_scale(S.cp.leaf[l].x, S.cst[l], S.ivar[l], p, b.quirks);
+    }
+  }
+}
+
+// grad_part holds GP_PER_TILE entries per (slot, tile): the fused kernel writes one per 128 x 64 half tile, the
+// stand-alone kernels fill entry 0 and clear entry 1; finalize_kernel sums all of them in index order.
+constexpr int GP_PER_TILE = 2;
+
 template <int LMAX, int E>
 __global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_grad_kernel(Batch b, int kind) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef PolySmem<LMAX> SM;
   SM& S = *reinterpret_cast<SM*>(smem_raw);
   const unsigned sb = (unsigned)__cvta_generic_to_shared(smem_raw);
-  constexpr int NV = 3 * LMAX + 1;
   const int count = b.kcount[kind];
   const int* list = b.klist + kind * b.list_stride;
   const int ntiles = tri_count(b.T);
   const long long nwork = (long long)count * ntiles;
-  const int c = threadIdx.x & (NB - 1), h = threadIdx.x >> 7;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
     const int slot = list[w / ntiles];
     if (b.slot_status[slot] != 0) continue;
     const int tile = (int)(w % ntiles);
     int ti, tj;
     tri_decode(tile, ti, tj);
-    double Aj[LMAX], Sj[LMAX], Cj[LMAX];
-    int ops[LMAX];
-    poly_prologue<LMAX>(S, b, slot, ti, tj, Aj, Sj, Cj, ops);
-    if (threadIdx.x >= NB) S.ai[c] = b.alpha[(size_t)slot * b.Np + ti * NB + c];
-    const double aj = b.alpha[(size_t)slot * b.Np + tj * NB + c];
-    __syncthreads();
-    const int L = S.cp.L, G = S.cp.G, single = S.cp.single;
-    const unsigned terms4 = *reinterpret_cast<const unsigned*>(S.cp.term);
-    double acc[LMAX][3], accn = 0.0;
-#pragma unroll
-    for (int l = 0; l < LMAX; l++) { acc[l][0] = 0.0; acc[l][1] = 0.0; acc[l][2] = 0.0; }
-    const double* Kinv = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB + c;
-    const int gj = tj * NB + c;
-    // diagonal tiles: rows above this warp's first column hold no lower-triangle element
-    int rbeg = h * 64;
-    if (ti == tj) { const int cmin = c - lane; if (cmin > rbeg) rbeg = cmin / E * E; }
-    const int rend = h * 64 + 64;
-    double kv[E];
-#pragma unroll
-    for (int e = 0; e < E; e++) kv[e] = (rbeg < rend) ? Kinv[(size_t)(rbeg + e) * b.Np] : 0.0;
-#pragma unroll 1
-    for (int r0 = rbeg; r0 < rend; r0 += E) {
-      double wt[E], ar[E];
-      lds_rows<E>(sb + (unsigned)offsetof(SM, ai) + r0 * 8, ar);
-#pragma unroll
-      for (int e = 0; e < E; e++) {
-        const int gi = ti * NB + r0 + e;
-        double wv = 0.5 * (ar[e] * aj - kv[e]);
-        const bool valid = gi < b.N && gj <= gi;       // gj <= gi < N
-        if (gi == gj) { if (valid) accn += wv; } else wv *= 2.0;      // symmetric pair (i, j), (j, i)
-        wt[e] = valid ? wv : 0.0;
-      }
-      if (r0 + E < rend) {
-#pragma unroll
-        for (int e = 0; e < E; e++) kv[e] = Kinv[(size_t)(r0 + E + e) * b.Np];
-      }
-      double v[LMAX][E], aux[LMAX][E];
-#pragma unroll
-      for (int l = 0; l < LMAX; l++)
-        if (l < L) {
-          double Ar[E];
-          lds_rows<E>(sb + (unsigned)offsetof(SM, Ai) + (l * NB + r0) * 8, Ar);
-          leaf_fwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, Ar, sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8,
-                      sb + (unsigned)offsetof(SM, Ci) + (l * NB + r0) * 8, Aj[l], Sj[l], Cj[l], v[l], aux[l]);
-        }
-#pragma unroll
-      for (int l = 0; l < LMAX; l++)
-        if (l < L) {
-          double g[E];
-          if (single) {
-#pragma unroll
-            for (int e = 0; e < E; e++) g[e] = wt[e];
-          } else {
-            double adj[E];
-#pragma unroll
-            for (int e = 0; e < E; e++) adj[e] = 0.0;
-            for (int t = 0; t < G; t++) {
-              const unsigned mask = term_mask<LMAX>(terms4, sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), t);
-              if (!(mask & (1u << l))) continue;
-              double p[E];
-              mask_product<LMAX, E>(v, mask & ~(1u << l), p);
-#pragma unroll
-              for (int e = 0; e < E; e++) adj[e] += p[e];
-            }
-#pragma unroll
-            for (int e = 0; e < E; e++) g[e] = wt[e] * adj[e];
-          }
-          double Ar[E];
-          lds_rows<E>(sb + (unsigned)offsetof(SM, Ai) + (l * NB + r0) * 8, Ar);
-          leaf_bwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, Ar, sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8,
-                      sb + (unsigned)offsetof(SM, Ci) + (l * NB + r0) * 8, Aj[l], Sj[l], Cj[l], g, v[l], aux[l], acc[l]);
-        }
-    }
-    // CTA reduction in a fixed order: lanes (shuffle tree), then the 8 warps
-#pragma unroll
-    for (int i = 0; i < NV; i++) {
-      double x = (i == NV - 1) ? accn : acc[i / 3][i % 3];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-      if (lane == 0) S.red[warp][i] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x < NV) {
-      const int i = threadIdx.x;
-      double s = 0.0;
-#pragma unroll
-      for (int q = 0; q < 8; q++) s += S.red[q][i];
-      double* out = b.grad_part + ((size_t)slot * ntiles + tile) * b.pstride;
-      if (i == NV - 1) out[S.cp.nparam] = s;
-      else {
-        const int l = i / 3, p = i % 3;
-        if (l < L && p < S.cp.leaf[l].w)
-          out[S.cp.leaf[l].z + p] = s * leaf_grad_scale(S.cp.leaf[l].x, S.cst[l], S.ivar[l], p, b.quirks);
-      }
-    }
+    double* out = b.grad_part + ((size_t)slot * ntiles + tile) * GP_PER_TILE * b.pstride;
+    if (threadIdx.x < b.pstride) out[b.pstride + threadIdx.x] = 0.0;
+    poly_grad_tile<LMAX, E, NB>(S, sb, b, slot, ti, tj, 0, b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB, b.Np, out);
   }
+}
+
+// Fused K^-1 + gradient for the <= 4-leaf programs: the K^-1 half tile a CTA has just accumulated on the DMMA pipe is
+// staged in the (now idle) pipeline buffers and contracted with dK/dtheta right there.  K^-1 never goes to HBM, and the
+// element-wise FP64 work of one CTA runs while the co-resident CTA of the SM is in its DMMA main loop -- the FP64 ALU
+// and the DMMA path are one datapath on B200 (tools/pipe_probe), so this fills the bubbles both kernels had on their own
+// (kinv_kernel: pipe 83 % busy; poly_grad_kernel: 43 %).  Slots of other kinds get K^-1 stored as before.
+constexpr int KG_LD = TG_TN + 2;         // row length of the staged 128 x 64 half tile
+static_assert(NB * KG_LD * 8 + sizeof(PolySmem<4>) <= TG_SMEM_BYTES, "staged tile + gradient tables fit the pipeline buffers");
+
+__global__ void __launch_bounds__(TG_THREADS, 2) kinv_grad_kernel(Batch b) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int bx = blockIdx.x >> 1, hf = blockIdx.x & 1;
+  const int slot = b.slot0 + blockIdx.y;
+  double acc[TG_MT][TG_NT][2];
+  GemmOut o;
+  if (!gemm_compute<GM_KINV>(b, 0, UpdRange{0, 0, 0, 0}, bx, hf, reinterpret_cast<double*>(smem_raw), acc, o)) return;
+  if (b.cprog[slot].kind != CK_POLY4) {      // uniform per CTA
+    gemm_store(acc, o);
+    return;
+  }
+  __syncthreads();                           // every warp has left the pipeline stages
+  double* Kt = reinterpret_cast<double*>(smem_raw);
+  if (!o.skip) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int wm, wn;
+    warp_coords(warp, wm, wn);
+    double* dst = Kt + (wm * 32 + (lane >> 2)) * KG_LD + wn * 32 + (lane & 3) * 2;
+#pragma unroll
+    for (int mt = 0; mt < TG_MT; mt++)
+#pragma unroll
+      for (int nt = 0; nt < TG_NT; nt++)
+        *reinterpret_cast<double2*>(dst + (mt * 8) * KG_LD + nt * 8) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+  }
+  // (poly_grad_tile starts with a barrier: the staged tile is complete before anybody reads it)
+  PolySmem<4>& S = *reinterpret_cast<PolySmem<4>*>(smem_raw + NB * KG_LD * 8);
+  const unsigned sb = (unsigned)__cvta_generic_to_shared(&S);
+  int ti, tj;
+  tri_decode(bx, ti, tj);
+  const int ntiles = tri_count(b.T);
+  double* out = b.grad_part + (((size_t)slot * ntiles + bx) * GP_PER_TILE + hf) * b.pstride;
+  poly_grad_tile<4, POLY_E4, TG_TN>(S, sb, b, slot, ti, tj, hf * TG_TN, Kt, KG_LD, out);
+}
+
+void launch_kinv_grad(const Batch& b, cudaStream_t s) {
+  dim3 grid(2 * tri_count(b.T), b.nslots);
+  kinv_grad_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b);
+  g_launch_count++;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -650,22 +724,17 @@ __global__ void __launch_bounds__(256) interp_grad_kernel(Batch b) {
       if (lane == 0) wred[warp * b.pstride + p] = v;
     }
     __syncthreads();
-    double* out = b.grad_part + ((size_t)slot * ntiles + tile) * b.pstride;
+    double* out = b.grad_part + ((size_t)slot * ntiles + tile) * GP_PER_TILE * b.pstride;
     for (int p = threadIdx.x; p <= np; p += blockDim.x) {
       double s = 0.0;
 #pragma unroll
       for (int q = 0; q < 8; q++) s += wred[q * b.pstride + p];
       out[p] = s;
+      out[b.pstride + p] = 0.0;
     }
   }
 }
 
-#ifndef POLY_E4
-#define POLY_E4 2
-#endif
-#ifndef POLY_E8
-#define POLY_E8 1
-#endif
 
 void launch_build_k(const Batch& b, cudaStream_t s) {
   poly_build_kernel<4, POLY_E4><<<g_grid_poly_build[0], 256, sizeof(PolySmem<4>), s>>>(b, CK_POLY4);
@@ -674,8 +743,8 @@ void launch_build_k(const Batch& b, cudaStream_t s) {
   g_launch_count += 3;
 }
 
-void launch_grad(const Batch& b, cudaStream_t s) {
-  poly_grad_kernel<4, POLY_E4><<<g_grid_poly_grad[0], 256, sizeof(PolySmem<4>), s>>>(b, CK_POLY4);
+void launch_grad(const Batch& b, cudaStream_t s, bool poly4_done) {
+  if (!poly4_done) poly_grad_kernel<4, POLY_E4><<<g_grid_poly_grad[0], 256, sizeof(PolySmem<4>), s>>>(b, CK_POLY4);
   poly_grad_kernel<8, POLY_E8><<<g_grid_poly_grad[1], 256, sizeof(PolySmem<8>), s>>>(b, CK_POLY8);
   const size_t smem = sizeof(ElemSmem) + 8 * (size_t)b.pstride * sizeof(double);
   interp_grad_kernel<<<g_grid_interp_grad, 256, smem, s>>>(b);
@@ -733,7 +802,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(Batch b, int with_grad) {
     if (!(fabs(lml) < 1.7e308)) bad = 1;
   }
   if (with_grad) {
-    const int ntiles = tri_count(b.T);
+    const int ntiles = tri_count(b.T) * GP_PER_TILE;
     const double* gp = b.grad_part + (size_t)slot * ntiles * b.pstride;
     // one warp per parameter: lane l sums tiles l, l + 32, ... in order, then a fixed shuffle tree (the order never
     // depends on the batch around this item)
@@ -798,6 +867,8 @@ int configure_kernels() {
     if (e != cudaSuccess) return (int)e;
     *c.grid = g_sm_count * (per_sm > 0 ? per_sm : 1);
   }
+  e = cudaFuncSetAttribute(kinv_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
   return configure_chol_kernels();
 }
 

@@ -21,7 +21,7 @@ struct Batch {
   double* alpha;             // [slot][Np]  K^-1 y
   double* logdet_part;       // [slot][T]
   double* diag_part;         // [slot][T]   partial sums of diag(K_y) (jitter ladder)
-  double* grad_part;         // [slot][ntiles][pstride]
+  double* grad_part;         // [slot][ntiles][2][pstride]: gradient partials per 128 x 64 half tile (elem_kernels.cu GP_PER_TILE)
   double* solve_part;        // [slot][ntiles][NB] tile partials of z = V^T y, then of alpha = V z
   int pstride;
   int* slot_status;          // [slot] 0 ok, >0 = 1-based index of first bad pivot
@@ -66,7 +66,8 @@ void launch_gemm(const Batch& b, int mode, int step, cudaStream_t s);
 void launch_update(const Batch& b, UpdRange r, cudaStream_t s);
 void launch_vupdate(const Batch& b, UpdRange r, cudaStream_t s);
 void launch_solve(const Batch& b, cudaStream_t s);                          // z = L^-1 y, alpha = L^-T z
-void launch_grad(const Batch& b, cudaStream_t s);
+void launch_kinv_grad(const Batch& b, cudaStream_t s);                     // K^-1 fused with the gradient of the <= 4-leaf programs
+void launch_grad(const Batch& b, cudaStream_t s, bool poly4_done);          // poly4_done: launch_kinv_grad covered the <= 4-leaf programs
 void launch_finalize(const Batch& b, int with_grad, cudaStream_t s);
 int configure_kernels();
 extern std::atomic<long long> g_launch_count;                                            // kernels launched (host-side counter)                                                    // opt-in shared memory sizes

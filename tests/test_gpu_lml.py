@@ -129,3 +129,31 @@ def test_jitter_ladder_and_not_pd(engine):
     assert np.max(np.abs(dlml[a:b] - ref_g)) <= 1e-6 * max(1.0, np.max(np.abs(ref_g)))
     assert status[1] == 0 and tries[1] == 0
     assert status[2] == 2 and np.isnan(lml[2])
+
+
+def test_fused_kinv_gradient_kernel_matches_oracle(engine):
+    """b200gp_set_fused_grad(1): K^-1 tile staged in shared memory and contracted in the same kernel (<= 4 leaves),
+    other kinds keep the two-kernel path inside the same batch."""
+    from ms_project_b200.program import ProgramBatch
+    from oracle import gp
+    X, y = make_data(300, 3, seed=11)
+    kernels = [from_string(s) for s in KERNELS]
+    batch = ProgramBatch(kernels)
+    engine.bind(X, y, slots=len(kernels), max_params=batch.max_params)
+    engine.upload_programs(batch)
+    theta, ks, nz = random_theta(batch, np.random.RandomState(5))
+    engine.set_fused_grad(True)
+    try:
+        lml, dlml, status, tries = engine.lml_grad(batch, theta)
+        lml, dlml, status = lml.copy(), dlml.copy(), status.copy()
+    finally:
+        engine.set_fused_grad(False)
+    lml2, dlml2, _, _ = engine.lml_grad(batch, theta)
+    for i, k in enumerate(kernels):
+        ref_lml, ref_g, _ = gp.lml_and_grad(to_oracle_expr(k), ks[i], nz[i], X, y)
+        a, b = batch.theta_off[i], batch.theta_off[i + 1]
+        assert status[i] == 0
+        assert lml[i] == lml2[i]                                   # the factorisation does not depend on the mode
+        scale = max(1.0, np.max(np.abs(ref_g)))
+        assert np.max(np.abs(dlml[a:b] - ref_g)) <= 1e-6 * scale, (KERNELS[i], dlml[a:b], ref_g)
+        assert np.max(np.abs(dlml[a:b] - dlml2[a:b])) <= 1e-10 * scale
