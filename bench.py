@@ -125,9 +125,9 @@ def cpu_reference_rate(X, y, items, thetas, noises, budget_s, max_items):
     return done / dt, cores, done, dt
 
 
-def fit_rate(eng, X, y, items, n_candidates=64):
-    """Secondary figure: FULLY FITTED candidates / s (optimize_restarts with 3 restarts, L-BFGS-B maxfun 1000) for the
-    first `n_candidates` C2 kernels, through the public scoring API (GPModel batch seam), BOMS hyperpriors."""
+def fit_rate(eng, X, y, items, n_candidates=N_KERNELS):
+    """Secondary figure: FULLY FITTED candidates / s (optimize_restarts with 3 restarts, L-BFGS-B maxfun 1000) of the
+    whole C2 configuration (256 kernels), through the public scoring API (GPModel batch seam), BOMS hyperpriors."""
     from ms_project_b200 import fitness, workloads
     from ms_project_b200.covariance import Covariance
     from ms_project_b200.gp_model import GPModel, score_models

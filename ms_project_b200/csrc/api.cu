@@ -290,7 +290,7 @@ static int la_panel_width(const b200gp_ctx* c, const Batch& b) {
 template <typename PanelFn, typename UpdateFn>
 static void panel_schedule(b200gp_ctx* c, const Batch& b, PanelFn panel, UpdateFn update) {
   const int T = b.T;
-  const bool la = (b.nslots < c->la_slots && T >= 8);
+  const bool la = (b.nslots < c->la_slots && T >= 2);
   if (!la) {
     const int W = c->batch_panel_tiles;
     const bool split = b.nslots >= 16;
@@ -383,7 +383,7 @@ static void inverse_phase(b200gp_ctx* c, const Batch& b) {
 // on 148 SMs and the evaluation time is the length of the dependency chain, not the flops.  Panel p of L^-T only needs
 // panel p of L, so it runs on a third stream as soon as the Cholesky has finished that panel, hidden behind the (longer)
 // chain of the next Cholesky panel.
-static bool pipelined_inverse(const b200gp_ctx* c, const Batch& b) { return b.nslots < c->la_slots && b.T >= 8 && b.T <= 32; }
+static bool pipelined_inverse(const b200gp_ctx* c, const Batch& b) { return b.nslots < c->la_slots && b.T >= 2 && b.T <= 32; }
 
 static void cholesky_inverse_pipelined(b200gp_ctx* c, const Batch& b) {
   const int T = b.T, W = la_panel_width(c, b);
