@@ -22,8 +22,17 @@
 #ifndef POLY_E4
 #define POLY_E4 2
 #endif
+#ifndef POLY_BUILD_CTAS
+#define POLY_BUILD_CTAS 3      // resident CTAs per SM the <= 4-leaf kernels are compiled for (register cap 85: 78 used, no spills; 5.7 -> 5.1 ms per 256 items)
+#endif
+#ifndef POLY_GRAD_CTAS
+#define POLY_GRAD_CTAS 2
+#endif
 #ifndef POLY_E8
 #define POLY_E8 1
+#endif
+#ifndef POLY_GE4
+#define POLY_GE4 POLY_E4       // rows interleaved by the gradient kernels (kept apart from the build kernel's for tuning)
 #endif
 
 namespace b200gp {
@@ -365,7 +374,7 @@ __device__ __forceinline__ unsigned term_mask(unsigned terms4, unsigned term_add
 }
 
 template <int LMAX, int E>
-__global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_build_kernel(Batch b, int kind) {
+__global__ void __launch_bounds__(256, LMAX == 4 ? POLY_BUILD_CTAS : 1) poly_build_kernel(Batch b, int kind) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef PolySmem<LMAX> SM;
   SM& S = *reinterpret_cast<SM*>(smem_raw);
@@ -543,7 +552,7 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
 constexpr int GP_PER_TILE = 2;
 
 template <int LMAX, int E>
-__global__ void __launch_bounds__(256, LMAX == 4 ? 2 : 1) poly_grad_kernel(Batch b, int kind) {
+__global__ void __launch_bounds__(256, LMAX == 4 ? POLY_GRAD_CTAS : 1) poly_grad_kernel(Batch b, int kind) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef PolySmem<LMAX> SM;
   SM& S = *reinterpret_cast<SM*>(smem_raw);
@@ -603,7 +612,7 @@ __global__ void __launch_bounds__(TG_THREADS, 2) kinv_grad_kernel(Batch b) {
   tri_decode(bx, ti, tj);
   const int ntiles = tri_count(b.T);
   double* out = b.grad_part + (((size_t)slot * ntiles + bx) * GP_PER_TILE + hf) * b.pstride;
-  poly_grad_tile<4, POLY_E4, TG_TN>(S, sb, b, slot, ti, tj, hf * TG_TN, Kt, KG_LD, out);
+  poly_grad_tile<4, POLY_GE4, TG_TN>(S, sb, b, slot, ti, tj, hf * TG_TN, Kt, KG_LD, out);
 }
 
 void launch_kinv_grad(const Batch& b, cudaStream_t s) {
@@ -744,7 +753,7 @@ void launch_build_k(const Batch& b, cudaStream_t s) {
 }
 
 void launch_grad(const Batch& b, cudaStream_t s, bool poly4_done) {
-  if (!poly4_done) poly_grad_kernel<4, POLY_E4><<<g_grid_poly_grad[0], 256, sizeof(PolySmem<4>), s>>>(b, CK_POLY4);
+  if (!poly4_done) poly_grad_kernel<4, POLY_GE4><<<g_grid_poly_grad[0], 256, sizeof(PolySmem<4>), s>>>(b, CK_POLY4);
   poly_grad_kernel<8, POLY_E8><<<g_grid_poly_grad[1], 256, sizeof(PolySmem<8>), s>>>(b, CK_POLY8);
   const size_t smem = sizeof(ElemSmem) + 8 * (size_t)b.pstride * sizeof(double);
   interp_grad_kernel<<<g_grid_interp_grad, 256, smem, s>>>(b);
@@ -854,7 +863,7 @@ int configure_kernels() {
   const Cfg cfgs[] = {
       {(const void*)poly_build_kernel<4, POLY_E4>, (int)sizeof(PolySmem<4>), &g_grid_poly_build[0]},
       {(const void*)poly_build_kernel<8, POLY_E8>, (int)sizeof(PolySmem<8>), &g_grid_poly_build[1]},
-      {(const void*)poly_grad_kernel<4, POLY_E4>, (int)sizeof(PolySmem<4>), &g_grid_poly_grad[0]},
+      {(const void*)poly_grad_kernel<4, POLY_GE4>, (int)sizeof(PolySmem<4>), &g_grid_poly_grad[0]},
       {(const void*)poly_grad_kernel<8, POLY_E8>, (int)sizeof(PolySmem<8>), &g_grid_poly_grad[1]},
       {(const void*)interp_build_kernel, (int)sizeof(ElemSmem), &g_grid_interp_build},
       {(const void*)interp_grad_kernel, interp_grad_smem, &g_grid_interp_grad},
