@@ -5,7 +5,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get('B200GP_LIB') or os.path.join(_HERE, 'libb200gp.so')      # B200GP_LIB: variant builds of tuning experiments
+LIB_PATH = os.path.join(_HERE, 'libb200gp.so')
 CSRC = os.path.join(_HERE, 'csrc')
 
 _lib = None

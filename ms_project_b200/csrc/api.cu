@@ -1,7 +1,6 @@
 // C-ABI of libb200gp (include/b200gp.h): context, workspace carving, phase orchestration, jitter ladder.
 #include <cmath>
 #include <cstdarg>
-#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -153,8 +152,6 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
   cudaEventCreateWithFlags(&c->evR, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->evS, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->evI, cudaEventDisableTiming);
-  if (const char* e = getenv("B200GP_FUSED_GRAD")) c->fused_grad = atoi(e) != 0;                                          // tuning aid
-  if (const char* e = getenv("B200GP_LA_SLOTS")) { const int v = atoi(e); if (v >= 0 && v <= 4096) c->la_slots = v; }   // tuning aid
   *out = c;
   return 0;
 }
