@@ -136,6 +136,7 @@ struct PolySmem {
   double ai[NB];                // alpha_i (gradient pass) / diagonal staging (build)
   double red[8][3 * LMAX + 1];
   double noise;
+  double etab[64];              // copy of FM_EXPTAB (fastmath.cuh exp_tab)
 };
 
 // Explicit shared-window loads: the hot loops address PolySmem by 32-bit offsets from one base register instead of
@@ -181,13 +182,13 @@ __device__ __forceinline__ void point_values(int op, const double* cst, double x
 // sin / cos rows); aux keeps what the reverse sweep cannot cheaply recompute.  Straight-line math (fastmath.cuh) so
 // the E chains interleave.
 template <int E>
-__device__ __forceinline__ void leaf_fwd(int op, unsigned cst, const double (&Ar)[E], unsigned srow, unsigned crow,
+__device__ __forceinline__ void leaf_fwd(int op, unsigned cst, unsigned etab, const double (&Ar)[E], unsigned srow, unsigned crow,
                                          double Aj, double Sj, double Cj, double (&v)[E], double (&aux)[E]) {
   double c0, c1;
   lds_v2(cst, c0, c1);
   if (op == OP_SE) {            // rbf.ipynb#1-2: v exp(-r^2 / 2)
 #pragma unroll
-    for (int e = 0; e < E; e++) { const double r = (Ar[e] - Aj) * c1; const double a = r * r; aux[e] = a; v[e] = c0 * exp_sl(-0.5 * a); }
+    for (int e = 0; e < E; e++) { const double r = (Ar[e] - Aj) * c1; const double a = r * r; aux[e] = a; v[e] = c0 * exp_tab(-0.5 * a, etab); }
   } else if (op == OP_RQ) {     // rational-quadratic.ipynb#2: v exp(-a log1p(r^2 / 2a))
     double c2, c3;
     lds_v2(cst + 16, c2, c3);
@@ -196,7 +197,7 @@ __device__ __forceinline__ void leaf_fwd(int op, unsigned cst, const double (&Ar
       const double r = (Ar[e] - Aj) * c1;
       const double lg = log1p_pos((r * r) * c3);
       aux[e] = lg;
-      v[e] = c0 * exp_sl(-c2 * lg);
+      v[e] = c0 * exp_tab(-c2 * lg, etab);
     }
   } else if (op == OP_PER) {    // periodic.ipynb#2: v exp(-2 sin^2(pi (x - x') / p) / l^2); sin(a_i - a_j) by the angle-difference identity
     const double il = lds_f64(cst + 16);
@@ -208,7 +209,7 @@ __device__ __forceinline__ void leaf_fwd(int op, unsigned cst, const double (&Ar
       const double s = Sr[e] * Cj - Cr[e] * Sj;
       const double q = s * il;
       aux[e] = s;
-      v[e] = c0 * exp_sl(-2.0 * (q * q));
+      v[e] = c0 * exp_tab(-2.0 * (q * q), etab);
     }
   } else if (op == OP_LIN) {    // linear.ipynb#2: v (x - c)(x' - c)
 #pragma unroll
@@ -298,6 +299,7 @@ __device__ __forceinline__ void poly_prologue(PolySmem<LMAX>& S, const Batch& b,
   const int L = S.cp.L;
   if (threadIdx.x < L) leaf_constants(S.cp.leaf[threadIdx.x].x, b.theta + th0 + S.cp.leaf[threadIdx.x].z, S.cst[threadIdx.x], S.ivar[threadIdx.x]);
   if (threadIdx.x == 32) S.noise = b.theta[b.theta_off[item + 1] - 1];
+  if (threadIdx.x >= 64 && threadIdx.x < 128) S.etab[threadIdx.x - 64] = FM_EXPTAB[threadIdx.x - 64];
   __syncthreads();
   if (threadIdx.x < NB) {        // row-side tables of the 128 rows of tile row ti
     const int r = threadIdx.x;
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? POLY_BUILD_CTAS : 1) poly_bui
         if (l < L) {
           double Ar[E];
           lds_rows<E>(sb + (unsigned)offsetof(SM, Ai) + (l * NB + r0) * 8, Ar);
-          leaf_fwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, Ar, sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8,
+          leaf_fwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, sb + (unsigned)offsetof(SM, etab), Ar, sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8,
                       sb + (unsigned)offsetof(SM, Ci) + (l * NB + r0) * 8, Aj[l], Sj[l], Cj[l], v[l], aux);
         }
       double k[E];
@@ -493,7 +495,7 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
       if (l < L) {
         double Ar[E];
         lds_rows<E>(sb + (unsigned)offsetof(SM, Ai) + (l * NB + r0) * 8, Ar);
-        leaf_fwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, Ar, sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8,
+        leaf_fwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, sb + (unsigned)offsetof(SM, etab), Ar, sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8,
                     sb + (unsigned)offsetof(SM, Ci) + (l * NB + r0) * 8, Aj[l], Sj[l], Cj[l], v[l], aux[l]);
       }
 #pragma unroll
