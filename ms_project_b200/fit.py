@@ -14,7 +14,7 @@ import numpy as np
 
 from .gpy_compat.priors import Gaussian as _GaussianPrior, LogGaussian as _LogGaussianPrior
 from .gpy_compat.transformations import Logexp
-from .optimizer import LBFGSB
+from .optimizer import make_optimizer
 from .program import ProgramBatch
 
 F_MAX = np.finfo(np.float64).max
@@ -24,11 +24,10 @@ _LOGEXP = Logexp()
 
 def check_optimizer(optimizer):
     """paramz resolves `optimizer=None` to its preferred optimiser, L-BFGS-B, which is what every experiment
-    JSON of the reference uses (training/experiments/*/*.json: "optimizer": null).  Other paramz optimisers
-    (scg, tnc, simplex...) have no batched driver here and are rejected loudly."""
-    if optimizer is None or str(optimizer).lower() in ('lbfgsb', 'lbfgs', 'bfgs', 'l-bfgs-b'):
-        return
-    raise NotImplementedError("optimizer %r: only L-BFGS-B (optimizer=None / 'lbfgsb') is implemented" % (optimizer,))
+    JSON of the reference uses (training/experiments/*/*.json: "optimizer": null); 'scg' is the default of
+    CKSModelSelector (cks_model_selector.py:21).  Both have batched ask/tell drivers (optimizer.py); other paramz
+    optimisers (tnc, simplex, ...) are rejected loudly."""
+    make_optimizer(optimizer, np.zeros(1))
 
 
 class _PriorTable(object):
@@ -107,7 +106,7 @@ def draw_starts(kernels, likelihoods, num_restarts):
 
 
 def fit_models(engine, kernels, likelihoods, num_restarts=10, max_iters=1000, robust=True, verbose=False,
-               on_iteration=None, starts=None):
+               on_iteration=None, starts=None, optimizer=None):
     """optimize_restarts for M models at once on `engine` (already bound to X, y).
 
     kernels / likelihoods are modified in place (the optimum is written back, as GPModel.fit does with
@@ -137,7 +136,7 @@ def fit_models(engine, kernels, likelihoods, num_restarts=10, max_iters=1000, ro
 
     theta = np.concatenate(starts)
     x0 = _LOGEXP.finv(theta)
-    opts = [LBFGSB(x0[off[j]:off[j + 1]], maxfun=max_iters, maxiter=max_iters) for j in range(n_inst)]
+    opts = [make_optimizer(optimizer, x0[off[j]:off[j + 1]], max_iters=max_iters) for j in range(n_inst)]
     x_all = x0.copy()
     stale = np.zeros_like(theta)            # last successfully computed dLML/dtheta per instance
     fail_count = np.zeros(n_inst, dtype=int)
@@ -178,7 +177,7 @@ def fit_models(engine, kernels, likelihoods, num_restarts=10, max_iters=1000, ro
                         raise np.linalg.LinAlgError('not positive definite, even with jitter.')
                     continue
                 fail_count[j] += 1
-                f, g = F_MAX, np.clip(g_x[a:b], -1e10, 1e10)
+                f, g = opts[j].fail_value, np.clip(g_x[a:b], -1e10, 1e10)
             o = opts[j]
             o.tell(f, g)
             x = o.ask()
@@ -230,7 +229,8 @@ def fit_models(engine, kernels, likelihoods, num_restarts=10, max_iters=1000, ro
     return results
 
 
-def fit_models_overlapped(engines, kernels, likelihoods, num_restarts=10, max_iters=1000, robust=True, starts=None):
+def fit_models_overlapped(engines, kernels, likelihoods, num_restarts=10, max_iters=1000, robust=True, starts=None,
+                          optimizer=None):
     """fit_models with the models split into len(engines) contiguous groups, each driven by its own host thread against
     its own engine (same GPU, private streams): while one group's L-BFGS-B steps run on the host (scipy holds the GIL),
     the other group's LML+gradient batch runs on the device (ctypes releases the GIL), and the tails of the two groups
@@ -240,7 +240,7 @@ def fit_models_overlapped(engines, kernels, likelihoods, num_restarts=10, max_it
     engines = list(engines)
     if len(engines) < 2 or M < 2 * len(engines):
         return fit_models(engines[0], kernels, likelihoods, num_restarts=num_restarts, max_iters=max_iters, robust=robust,
-                          starts=starts)
+                          starts=starts, optimizer=optimizer)
     import threading
     per_model = draw_starts(kernels, likelihoods, int(num_restarts)) if starts is None else starts
     bounds = np.linspace(0, M, len(engines) + 1).astype(int)
@@ -251,7 +251,7 @@ def fit_models_overlapped(engines, kernels, likelihoods, num_restarts=10, max_it
         lo, hi = int(bounds[g]), int(bounds[g + 1])
         try:
             results[g] = fit_models(engines[g], kernels[lo:hi], likelihoods[lo:hi], num_restarts=num_restarts,
-                                    max_iters=max_iters, robust=robust, starts=per_model[lo:hi])
+                                    max_iters=max_iters, robust=robust, starts=per_model[lo:hi], optimizer=optimizer)
         except BaseException as exc:          # re-raised in the caller's thread
             errors.append(exc)
 

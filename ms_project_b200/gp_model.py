@@ -149,11 +149,11 @@ def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engi
         for e in engines:
             e.ensure_bound(x, y, (n_inst + 1) // 2, maxp)
         results = fit_models_overlapped(engines, [g.kern for g in gps], [g.likelihood for g in gps], num_restarts=n_restarts,
-                                        robust=True, starts=starts)
+                                        robust=True, starts=starts, optimizer=optimizer)
     else:
         engine.ensure_bound(x, y, n_inst, maxp)
         results = fit_models(engine, [g.kern for g in gps], [g.likelihood for g in gps], num_restarts=n_restarts, robust=True,
-                             starts=starts)
+                             starts=starts, optimizer=optimizer)
     for g, r in zip(gps, results):
         g._lml, g._status = r.lml, r.status
         g.optimization_runs += r.runs
@@ -161,7 +161,7 @@ def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engi
     if retry:
         engine.ensure_bound(x, y, len(retry) * max(int(n_restarts), 1), maxp)
         rr = fit_models(engine, [gps[i].kern for i in retry], [gps[i].likelihood for i in retry], num_restarts=n_restarts,
-                        robust=True)
+                        robust=True, optimizer=optimizer)
         for i, r in zip(retry, rr):
             gps[i]._lml, gps[i]._status = r.lml, r.status
             if _is_bad(gps[i].log_likelihood()):

@@ -112,7 +112,7 @@ class GP(Parameterized):
         eng = self._engine()
         eng.ensure_bound(self.X, self.Y, max(int(num_restarts), 1), self.kern.size)
         res = fit_models(eng, [self.kern], [self.likelihood], num_restarts=num_restarts, max_iters=max_iters,
-                         robust=robust)[0]
+                         robust=robust, optimizer=optimizer)[0]
         self.optimization_runs += res.runs
         self._lml, self._status = res.lml, res.status
         return self.optimization_runs

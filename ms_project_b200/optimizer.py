@@ -1,4 +1,4 @@
-"""Ask/tell L-BFGS-B: the reference's optimiser, re-entrant.
+"""Ask/tell optimisers: the reference's L-BFGS-B and SCG, re-entrant.
 
 paramz `opt_lbfgsb` (the optimiser `optimize_restarts` uses when `optimizer=None`, reached from
 src/autoks/core/gp_model.py:64-65) calls `scipy.optimize.fmin_l_bfgs_b(f_fp, x0, maxfun=max_iters,
@@ -19,6 +19,7 @@ _INT = np.int64 if _ILP64 else np.int32
 
 class LBFGSB(object):
     """One unbounded L-BFGS-B minimisation (scipy defaults: m=10, factr=1e7, pgtol=1e-5, maxls=20)."""
+    fail_value = np.finfo(np.float64).max        # paramz Model._objective_grads on LinAlgError
 
     def __init__(self, x0, maxfun=1000, maxiter=1000, m=10, factr=1e7, pgtol=1e-5, maxls=20):
         x0 = np.asarray(x0, dtype=np.float64).ravel()
@@ -95,3 +96,138 @@ def minimize(fun_and_grad, x0, **kw):
         f, g = fun_and_grad(x.copy())
         opt.tell(f, g)
     return opt.result()
+
+
+class SCG(object):
+    """One scaled-conjugate-gradient minimisation as paramz runs it for `optimizer='scg'` -- the default optimiser of the
+    reference's CKSModelSelector (src/autoks/core/model_selection/cks_model_selector.py:21); paramz
+    optimization/scg.py:SCG driven by opt_SCG with maxiters = max_iters, max_f_eval = 1e4, xtol = ftol = 1e-6,
+    gtol = 1e-5.
+
+    paramz calls f (Model._objective) and gradf (Model._grads) separately; the device returns both from one evaluation,
+    so the gradient paramz would fetch at an accepted point is taken from the evaluation that produced its function value
+    (same numbers, one device evaluation fewer per successful iteration).  `funcalls` still counts what paramz would
+    have counted.  Same ask / tell / result protocol as LBFGSB; tests/test_optimizer.py checks identical iterates against
+    the sequential restatement oracle/scg.py."""
+    fail_value = np.inf                           # paramz Model._objective on LinAlgError
+
+    def __init__(self, x0, maxfun=1e4, maxiter=1000, xtol=1e-6, ftol=1e-6, gtol=1e-5):
+        self.x = np.array(x0, dtype=np.float64).ravel()
+        self.maxiter, self.max_f_eval = int(maxiter), maxfun
+        self.xtol, self.ftol, self.gtol = xtol, ftol, gtol
+        self.f = np.nan
+        self.nfev = 0          # device evaluations
+        self.funcalls = 0      # paramz's function_eval
+        self.nit = 0
+        self.status = 'Not converged'
+        self.done = False
+        self._waiting = False
+        self._reply = None
+        self._gen = self._run()
+        self._next = next(self._gen)
+
+    def ask(self):
+        if self.done:
+            return None
+        assert not self._waiting, 'tell() the pending evaluation first'
+        self._waiting = True
+        return self._next
+
+    def tell(self, f, g):
+        assert self._waiting
+        self._waiting = False
+        self.nfev += 1
+        try:
+            self._next = self._gen.send((float(f), np.asarray(g, dtype=np.float64).copy()))
+        except StopIteration:
+            self.done = True
+            self._next = None
+
+    def result(self):
+        return dict(x=self.x.copy(), f=float(self.f), funcalls=int(self.funcalls), nit=self.nit, warnflag=self.status)
+
+    def _run(self):
+        x = self.x
+        sigma0 = 1.0e-7
+        fold, gradnew = yield x                    # f(x) and gradf(x): two paramz calls, one evaluation
+        self.funcalls = 2
+        fnow = fold
+        self.f = fnow
+        gradold = gradnew.copy()
+        d = -gradnew
+        success = True
+        nsuccess = 0
+        beta, betamin, betamax = 1.0, 1.0e-15, 1.0e15
+        mu = kappa = theta = 0.0
+        iteration = 0
+        status = None
+        while iteration < self.maxiter:
+            if success:
+                mu = np.dot(d, gradnew)
+                if mu >= 0:
+                    d = -gradnew
+                    mu = np.dot(d, gradnew)
+                kappa = np.dot(d, d)
+                sigma = sigma0 / np.sqrt(kappa)
+                _, gplus = yield x + sigma * d     # gradf(xplus)
+                self.funcalls += 1
+                theta = np.dot(d, (gplus - gradnew)) / sigma
+            delta = theta + beta * kappa
+            if delta <= 0:
+                delta = beta * kappa
+                beta = beta - theta / kappa
+            alpha = -mu / delta
+            xnew = x + alpha * d
+            fnew, gnew = yield xnew                # f(xnew); its gradient is what gradf(x) returns if the step is accepted
+            self.funcalls += 1
+            if self.funcalls >= self.max_f_eval:
+                status = 'maximum number of function evaluations exceeded'
+                break
+            Delta = 2. * (fnew - fold) / (alpha * mu)
+            if Delta >= 0.:
+                success = True
+                nsuccess += 1
+                x = xnew
+                fnow = fnew
+            else:
+                success = False
+                fnow = fold
+            self.x, self.f = x, fnow
+            iteration += 1
+            self.nit = iteration
+            if success:
+                if np.abs(fnew - fold) < self.ftol:
+                    status = 'converged - relative reduction in objective'
+                    break
+                elif np.max(np.abs(alpha * d)) < self.xtol:
+                    status = 'converged - relative stepsize'
+                    break
+                else:
+                    gradold = gradnew
+                    gradnew = gnew
+                    self.funcalls += 1
+                    fold = fnew
+                    if np.dot(gradnew, gradnew) <= self.gtol:
+                        status = 'converged - relative reduction in gradient'
+                        break
+            if Delta < 0.25:
+                beta = min(4.0 * beta, betamax)
+            if Delta > 0.75:
+                beta = max(0.25 * beta, betamin)
+            if nsuccess == x.size:
+                d = -gradnew
+                beta = 1.
+                nsuccess = 0
+            elif success:
+                Gamma = np.dot(gradold - gradnew, gradnew) / mu
+                d = Gamma * d - gradnew
+        self.status = status if status is not None else 'maxiter exceeded'
+
+
+def make_optimizer(name, x0, max_iters=1000):
+    """The ask/tell optimiser paramz would pick for `optimizer=name` (None = its preferred one, L-BFGS-B)."""
+    if name is None or str(name).lower() in ('lbfgsb', 'lbfgs', 'bfgs', 'l-bfgs-b'):
+        return LBFGSB(x0, maxfun=max_iters, maxiter=max_iters)
+    if str(name).lower() == 'scg':
+        return SCG(x0, maxiter=max_iters)
+    raise NotImplementedError("optimizer %r: only L-BFGS-B (optimizer=None / 'lbfgsb') and 'scg' are implemented" % (name,))

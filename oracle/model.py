@@ -185,9 +185,42 @@ class OracleGP:
             g = np.clip(self._transform_gradients(self.objective_function_gradients()), -1e10, 1e10)
         return f, g
 
-    # -- optimisation (paramz Model.optimize / opt_lbfgsb)
-    def optimize(self, max_iters=1000):
+    def _objective(self, x):
+        """paramz Model._objective (what SCG calls for function values)."""
+        try:
+            self._set_optimizer_array(x)
+            obj = self.objective_function()
+            self._fail_count = 0
+        except (np.linalg.LinAlgError, ZeroDivisionError, ValueError):
+            if self._fail_count >= self.allowed_failures:
+                raise
+            self._fail_count += 1
+            return np.inf
+        return obj
+
+    def _grads(self, x):
+        """paramz Model._grads (what SCG calls for gradients)."""
+        try:
+            self._set_optimizer_array(x)
+            g = self._transform_gradients(self.objective_function_gradients())
+            self._fail_count = 0
+        except (np.linalg.LinAlgError, ZeroDivisionError, ValueError):
+            if self._fail_count >= self.allowed_failures:
+                raise
+            self._fail_count += 1
+            g = np.clip(self._transform_gradients(self.objective_function_gradients()), -1e10, 1e10)
+        return g
+
+    # -- optimisation (paramz Model.optimize / opt_lbfgsb / opt_SCG)
+    def optimize(self, max_iters=1000, optimizer=None):
         x0 = self.optimizer_array.copy()
+        if optimizer is not None and str(optimizer).lower() == 'scg':
+            from .scg import scg
+            x_opt, flog, nfev, status = scg(self._objective, self._grads, x0, maxiters=max_iters)
+            run = dict(x_opt=x_opt, f_opt=flog[-1], funcalls=nfev, warnflag=status, nit=len(flog) - 1)
+            self._set_optimizer_array_quiet(x_opt)
+            self.optimization_runs.append(run)
+            return run
         x_opt, _, info = optimize.fmin_l_bfgs_b(self._objective_grads, x0, maxfun=max_iters, maxiter=max_iters)
         f_opt = self._objective_grads(x_opt)[0]
         run = dict(x_opt=x_opt, f_opt=f_opt, funcalls=info['funcalls'], warnflag=info['warnflag'], nit=info['nit'])
@@ -221,7 +254,7 @@ class OracleGP:
         except np.linalg.LinAlgError:
             self._lml = np.nan
 
-    def optimize_restarts(self, num_restarts=10, rng=None, robust=True, max_iters=1000):
+    def optimize_restarts(self, num_restarts=10, rng=None, robust=True, max_iters=1000, optimizer=None):
         """paramz Model.optimize_restarts (sequential branch)."""
         rng = np.random if rng is None else rng
         initial_length = len(self.optimization_runs)
@@ -230,7 +263,7 @@ class OracleGP:
             try:
                 if i > 0:
                     self.randomize(rng)
-                self.optimize(max_iters=max_iters)
+                self.optimize(max_iters=max_iters, optimizer=optimizer)
             except Exception:
                 if not robust:
                     raise
@@ -242,14 +275,14 @@ class OracleGP:
         return self.optimization_runs
 
 
-def fit(expr, X, y, n_restarts=10, rng=None, **kw):
+def fit(expr, X, y, n_restarts=10, rng=None, optimizer=None, **kw):
     """GPModel.fit (src/autoks/core/gp_model.py:58-82): optimise; if LML is +-inf/NaN retry once;
     returns (model, failed_fitting)."""
     m = OracleGP(expr, X, y, **kw)
-    m.optimize_restarts(n_restarts, rng=rng)
+    m.optimize_restarts(n_restarts, rng=rng, optimizer=optimizer)
     failed = False
     if not np.isfinite(m.log_likelihood()):
-        m.optimize_restarts(n_restarts, rng=rng)
+        m.optimize_restarts(n_restarts, rng=rng, optimizer=optimizer)
         if not np.isfinite(m.log_likelihood()):
             failed = True
     return m, failed

@@ -23,13 +23,13 @@ def _with_priors(kernel):
     return kernel
 
 
-def _oracle_fit(kernels, X, y, n_restarts, seed, noise_prior=None):
+def _oracle_fit(kernels, X, y, n_restarts, seed, noise_prior=None, optimizer=None):
     rng = np.random.RandomState(seed)
     out = []
     for k in kernels:
         kp = [prior_tuple(p.prior) for p in k.flattened_parameters()]
-        m, failed = omodel.fit(to_oracle_expr(k), X, y, n_restarts=n_restarts, rng=rng, theta=k.param_array.copy(),
-                               kern_priors=kp, noise_prior=prior_tuple(noise_prior))
+        m, failed = omodel.fit(to_oracle_expr(k), X, y, n_restarts=n_restarts, rng=rng, optimizer=optimizer,
+                               theta=k.param_array.copy(), kern_priors=kp, noise_prior=prior_tuple(noise_prior))
         out.append((m, failed))
     return out
 
@@ -100,6 +100,31 @@ def test_fit_matches_oracle(engine, use_priors):
             assert np.allclose(got, om.param_array, rtol=1e-2, atol=1e-6), (name, got, om.param_array)
     assert np.allclose(scores, ref_scores, rtol=1e-6)
     assert list(np.argsort(scores)) == list(np.argsort(ref_scores))          # same ranking => same selected kernels
+
+
+def test_scg_fit_matches_oracle(engine):
+    """optimizer='scg' (the CKSModelSelector default, cks_model_selector.py:21): the batched ask/tell SCG against the
+    oracle's sequential restatement of paramz's SCG, same restart draws."""
+    from ms_project_b200 import workloads, fitness
+    from ms_project_b200.covariance import Covariance
+    from ms_project_b200.gp_model import GPModel, score_models
+    from ms_project_b200.gp_models import gp_regression
+    X, y = make_data(120, 2, seed=7)
+    names = ['SE_1', 'RQ_1 + SE_2', 'SE_1 * SE_2', 'LIN_1 + SE_2']
+    kernels = [_with_priors(from_string(s)) for s in names]
+    noise_prior = workloads.boms_hyperpriors()['GP']['variance']
+    ref = _oracle_fit([k.copy() for k in kernels], X, y, 2, seed=5, noise_prior=noise_prior, optimizer='scg')
+    md = gp_regression(likelihood_hyperprior={'variance': noise_prior})
+    models = [GPModel(Covariance(k)) for k in kernels]
+    np.random.seed(5)
+    scores = score_models(models, X, y, fitness.negative_bic, optimizer='scg', n_restarts=2, engine=engine, model_dict=md)
+    for (om, failed), m, name in zip(ref, models, names):
+        assert not failed and not m.failed_fitting
+        lml_ref = om.log_likelihood()
+        assert abs(m.fit_result.lml - lml_ref) <= 1e-5 * max(1.0, abs(lml_ref)), (name, m.fit_result.lml, lml_ref)
+        assert all(isinstance(r['warnflag'], str) for r in m.fit_result.runs)           # SCG status strings
+    ref_scores = [oscoring.negative_bic(om.log_likelihood(), X.shape[0], om._size_transformed()) for om, _ in ref]
+    assert list(np.argsort(scores)) == list(np.argsort(ref_scores))
 
 
 def test_first_evaluations_are_bitwise_reproducible(engine):

@@ -61,3 +61,54 @@ def test_lockstep_instances_are_independent():
                 pending[i] = nxt
     for o, r in zip(opts, refs):
         assert np.array_equal(o.x, r['x']) and o.nfev == r['funcalls']
+
+
+# ---- SCG: the ask/tell driver against the sequential restatement of paramz's SCG (oracle/scg.py)
+@pytest.mark.parametrize('fun,x0,maxiter', [
+    (rosen, np.array([-1.2, 1.0, 0.5, 2.0]), 1000),
+    (rosen, np.zeros(7), 12),
+    (quartic, np.linspace(-2, 2, 9), 1000),
+    (quartic, np.full(3, 0.3), 1000),
+])
+def test_scg_identical_to_sequential_restatement(fun, x0, maxiter):
+    from ms_project_b200.optimizer import SCG
+    from oracle.scg import scg
+    ref_x, flog, ref_nfe, ref_status = scg(lambda x: fun(x)[0], lambda x: fun(x)[1], x0.copy(), maxiters=maxiter)
+    opt = SCG(x0.copy(), maxiter=maxiter)
+    while True:
+        x = opt.ask()
+        if x is None:
+            break
+        f, g = fun(x.copy())
+        opt.tell(f, g)
+    res = opt.result()
+    assert np.array_equal(res['x'], ref_x)
+    assert res['f'] == flog[-1]
+    assert res['funcalls'] == ref_nfe and res['warnflag'] == ref_status and res['nit'] == len(flog) - 1
+    assert opt.nfev < ref_nfe                      # the gradient at an accepted point rides on its function evaluation
+
+
+def test_scg_failed_evaluations_are_rejected_steps():
+    """paramz returns inf for an objective that raised LinAlgError: the step is rejected and beta grows."""
+    from ms_project_b200.optimizer import SCG
+    opt = SCG(np.array([2.0, -1.0]), maxiter=50)
+    n = 0
+    while True:
+        x = opt.ask()
+        if x is None:
+            break
+        f, g = quartic(x.copy())
+        n += 1
+        if n in (3, 4):                            # two consecutive failures on function-value requests
+            f = SCG.fail_value
+        opt.tell(f, g)
+    assert np.isfinite(opt.result()['f']) and opt.result()['f'] < quartic(np.array([2.0, -1.0]))[0]
+
+
+def test_make_optimizer_names():
+    from ms_project_b200.optimizer import SCG, make_optimizer
+    assert isinstance(make_optimizer(None, np.zeros(2)), LBFGSB)
+    assert isinstance(make_optimizer('lbfgsb', np.zeros(2)), LBFGSB)
+    assert isinstance(make_optimizer('scg', np.zeros(2)), SCG)
+    with pytest.raises(NotImplementedError):
+        make_optimizer('tnc', np.zeros(2))
