@@ -140,6 +140,24 @@ int b200gp_centered_alignments(b200gp_ctx* ctx, const int32_t* d_prog, const int
 int b200gp_vector_pairs(b200gp_ctx* ctx, const double* d_G, int M, int S, int n, const int32_t* d_pair_i,
                         const int32_t* d_pair_j, int npairs, int metric, double* d_dist);
 
+/* Gram matrices and their log-determinants for `n` items over the bound X, through the scoring path's workspace slots
+ * (fused K-build + blocked DMMA Cholesky), for any N: what the distance builders need when the reference hands them
+ * more than B200GP_TILE points (it passes the whole training set: smbo_model_selector.py:91-97).
+ *   diag_mode 0: K;  1: K + (noise + 1e-8) I (exact inference);  2: K + noise I (Hellinger Gram matrices,
+ *   distance.py:186-190; the item's last theta entry is lambda_s)
+ *   d_K_out [n][N][N] symmetric copies or NULL;  d_logdet [items] / d_status [items] (1 = not positive definite) or NULL */
+int b200gp_gram_logdet(b200gp_ctx* ctx, const int32_t* d_prog, const int32_t* d_prog_off, const double* d_theta,
+                       const int32_t* d_theta_off, const int32_t* d_ids, int n, int diag_mode, double* d_K_out,
+                       double* d_logdet, int32_t* d_status);
+/* b200gp_hellinger_pairs for Gram matrices of any order n (= the N the context is bound to).  The caller lists the
+ * (pair, sample) cells whose log-determinants differ by more than the tolerance (hellinger_distance refactorises only
+ * those, distance.py:145-153) as d_work_pair[nwork] / d_work_s[nwork]; each costs one blocked Cholesky of
+ * 1/2 (G_i,s + G_j,s) in a workspace slot.  d_work: b200gp_hellinger_pairs_large_work_bytes(npairs, S) bytes. */
+size_t b200gp_hellinger_pairs_large_work_bytes(int npairs, int S);
+int b200gp_hellinger_pairs_large(b200gp_ctx* ctx, const double* d_logdet, const double* d_G, int M, int S, int n,
+                                 const int32_t* d_pair_i, const int32_t* d_pair_j, int npairs, const int32_t* d_work_pair,
+                                 const int32_t* d_work_s, int nwork, void* d_work, double* d_dist, int32_t* d_status);
+
 /* Phase timings (ms) of the most recent b200gp_lml_grad chunk, measured with CUDA events on the context
  * stream: [build_K, cholesky, inverse(V), solve, Kinv, grad+finalize].  Returns the number written. */
 int b200gp_last_phase_ms(b200gp_ctx* ctx, float* out, int cap);

@@ -75,6 +75,13 @@ def _declare(lib):
     lib.b200gp_hellinger_pairs.restype = ctypes.c_int
     lib.b200gp_hellinger_pairs.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int,
                                            ctypes.c_double, vp, vp, vp]
+    lib.b200gp_gram_logdet.restype = ctypes.c_int
+    lib.b200gp_gram_logdet.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]
+    lib.b200gp_hellinger_pairs_large_work_bytes.restype = ctypes.c_size_t
+    lib.b200gp_hellinger_pairs_large_work_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.b200gp_hellinger_pairs_large.restype = ctypes.c_int
+    lib.b200gp_hellinger_pairs_large.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int,
+                                                 vp, vp, ctypes.c_int, vp, vp, vp]
     lib.b200gp_vector_pairs.restype = ctypes.c_int
     lib.b200gp_vector_pairs.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, vp]
     lib.b200gp_centered_alignments.restype = ctypes.c_int
@@ -85,7 +92,8 @@ def _declare(lib):
 EXPORTS = ['b200gp_version', 'b200gp_create', 'b200gp_destroy', 'b200gp_last_error', 'b200gp_set_quirks', 'b200gp_set_lookup',
            'b200gp_set_profiling', 'b200gp_set_panel_tiles', 'b200gp_set_fused_grad', 'b200gp_launch_count', 'b200gp_last_phase_ms', 'b200gp_workspace_bytes',
            'b200gp_bind', 'b200gp_build_K', 'b200gp_lml_grad', 'b200gp_posterior', 'b200gp_potrf_work_bytes', 'b200gp_potrf',
-           'b200gp_hellinger_precompute', 'b200gp_hellinger_pairs_work_bytes', 'b200gp_hellinger_pairs', 'b200gp_vector_pairs', 'b200gp_centered_alignments', 'b200gp_alignment_min_slots']
+           'b200gp_hellinger_precompute', 'b200gp_hellinger_pairs_work_bytes', 'b200gp_hellinger_pairs', 'b200gp_gram_logdet', 'b200gp_hellinger_pairs_large_work_bytes',
+           'b200gp_hellinger_pairs_large', 'b200gp_vector_pairs', 'b200gp_centered_alignments', 'b200gp_alignment_min_slots']
 
 
 def lib():

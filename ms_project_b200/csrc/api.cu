@@ -18,6 +18,14 @@ void launch_hellinger_precompute(const double* Xsub, int n, int D, const int4* p
                                  double* logdet, double* G, int* status, cudaStream_t st);
 void launch_hellinger_pairs(const double* logdet, const double* G, int S, int n, const int* pair_i, const int* pair_j,
                             int npairs, double tol, double* h, int* hstatus, double* dist, int* status, cudaStream_t st);
+void launch_slot_logdet(const Batch& b, double* logdet, int* status, cudaStream_t st);
+void launch_havg_build(const Batch& b, const double* G, int S, int n, const int* pair_i, const int* pair_j,
+                       const int* work_pair, const int* work_s, cudaStream_t st);
+void launch_hpair_init(const double* logdet, int S, const int* pair_i, int npairs, double* ldpq, int* hstatus, cudaStream_t st);
+void launch_hpair_scatter(const Batch& b, int S, const int* work_pair, const int* work_s, double* ldpq, int* hstatus,
+                          cudaStream_t st);
+void launch_hpair_finish(const double* logdet, int S, const int* pair_i, const int* pair_j, int npairs, double* ldpq_h,
+                         int* hstatus, double* dist, int* status, cudaStream_t st);
 void launch_vector_pairs(const double* G, int S, int n, const int* pair_i, const int* pair_j, int npairs, int metric,
                          double* dist, cudaStream_t st);
 void launch_pack_data(const double* X, const double* y, int N, int D, int Np, double* Xt, double* yp, cudaStream_t s);
@@ -661,6 +669,71 @@ int b200gp_hellinger_pairs(b200gp_ctx* c, const double* logdet, const double* G,
   double* h = cv.take<double>((size_t)npairs * S);
   int* hs = cv.take<int>((size_t)npairs * S);
   launch_hellinger_pairs(logdet, G, S, n, pair_i, pair_j, npairs, tol_logdet, h, hs, dist, status, c->stream);
+  CUCHECK(c, cudaGetLastError());
+  return 0;
+}
+
+int b200gp_gram_logdet(b200gp_ctx* c, const int32_t* prog, const int32_t* prog_off, const double* theta,
+                       const int32_t* theta_off, const int32_t* ids, int n, int diag_mode, double* K_out, double* logdet,
+                       int32_t* status) {
+  if (!c) return -1;
+  if (!c->bound) return fail(c, "b200gp_gram_logdet: call b200gp_bind first");
+  if (!prog || !prog_off || !theta || !theta_off || !ids || (logdet && !status))
+    return fail(c, "b200gp_gram_logdet: null pointer");
+  if (diag_mode < 0 || diag_mode > 2) return fail(c, "b200gp_gram_logdet: diag_mode must be 0, 1 or 2");
+  if (!K_out && !logdet) return 0;
+  CUCHECK(c, cudaSetDevice(c->device));
+  const size_t n2 = (size_t)c->base.N * c->base.N;
+  for (int off = 0; off < n; off += c->slots) {
+    Batch b = c->base;
+    b.nslots = (n - off < c->slots) ? n - off : c->slots;
+    b.ids = ids + off;
+    b.prog = reinterpret_cast<const int4*>(prog); b.prog_off = prog_off; b.theta = theta; b.theta_off = theta_off;
+    b.quirks = c->quirks; b.lut = c->lut; b.lut_n = c->lut_n;
+    b.add_diag = diag_mode;
+    launch_compile(b, c->stream);
+    launch_build_k(b, c->stream);
+    if (K_out) launch_export_sym(b, K_out + (size_t)off * n2, c->stream);
+    if (logdet) {
+      CUCHECK(c, cudaMemsetAsync(b.slot_status, 0, sizeof(int) * b.nslots, c->stream));
+      cholesky_phase(c, b);
+      launch_slot_logdet(b, logdet, status, c->stream);
+    }
+  }
+  CUCHECK(c, cudaGetLastError());
+  return 0;
+}
+
+size_t b200gp_hellinger_pairs_large_work_bytes(int npairs, int S) {
+  if (npairs <= 0 || S <= 0) return 0;
+  return (size_t)npairs * S * (sizeof(double) + sizeof(int)) + 1024;
+}
+
+int b200gp_hellinger_pairs_large(b200gp_ctx* c, const double* logdet, const double* G, int M, int S, int n,
+                                 const int32_t* pair_i, const int32_t* pair_j, int npairs, const int32_t* work_pair,
+                                 const int32_t* work_s, int nwork, void* work, double* dist, int32_t* status) {
+  if (!c) return -1;
+  if (!c->bound) return fail(c, "b200gp_hellinger_pairs_large: call b200gp_bind (on the subset) first");
+  if (!logdet || !G || !pair_i || !pair_j || !dist || !status || !work || (nwork > 0 && (!work_pair || !work_s)))
+    return fail(c, "b200gp_hellinger_pairs_large: null pointer");
+  if (n != c->base.N) return fail(c, "b200gp_hellinger_pairs_large: the context is bound to %d points, the Gram matrices have %d", c->base.N, n);
+  if (M <= 0 || S <= 0 || nwork < 0) return fail(c, "b200gp_hellinger_pairs_large: bad geometry");
+  if (npairs <= 0) return 0;
+  CUCHECK(c, cudaSetDevice(c->device));
+  Carver cv(work);
+  double* ldpq = cv.take<double>((size_t)npairs * S);
+  int* hs = cv.take<int>((size_t)npairs * S);
+  cudaStream_t s = c->stream;
+  launch_hpair_init(logdet, S, pair_i, npairs, ldpq, hs, s);
+  for (int off = 0; off < nwork; off += c->slots) {
+    Batch b = c->base;
+    b.nslots = (nwork - off < c->slots) ? nwork - off : c->slots;
+    launch_havg_build(b, G, S, n, pair_i, pair_j, work_pair + off, work_s + off, s);
+    CUCHECK(c, cudaMemsetAsync(b.slot_status, 0, sizeof(int) * b.nslots, s));
+    cholesky_phase(c, b);
+    launch_hpair_scatter(b, S, work_pair + off, work_s + off, ldpq, hs, s);
+  }
+  launch_hpair_finish(logdet, S, pair_i, pair_j, npairs, ldpq, hs, dist, status, s);
   CUCHECK(c, cudaGetLastError());
   return 0;
 }

@@ -396,7 +396,8 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? POLY_BUILD_CTAS : 1) poly_bui
     __syncthreads();
     const int L = S.cp.L, G = S.cp.G;
     const unsigned terms4 = *reinterpret_cast<const unsigned*>(S.cp.term);
-    const double diag_add = b.add_diag ? S.noise + EXACT_INFERENCE_JITTER + (b.jitter ? b.jitter[slot] : 0.0) : 0.0;
+    const double diag_add = b.add_diag == 1 ? S.noise + EXACT_INFERENCE_JITTER + (b.jitter ? b.jitter[slot] : 0.0)
+                                             : (b.add_diag == 2 ? S.noise : 0.0);
     double* out = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB + c;
     const int gj = tj * NB + c;
 #pragma unroll 1
@@ -658,7 +659,8 @@ __global__ void __launch_bounds__(256) interp_build_kernel(Batch b) {
     load_program(S.P, b.prog, b.prog_off, b.theta, b.theta_off, item, b.lut, b.lut_n);
     stage_inputs(S, b, ti, tj);
     __syncthreads();
-    const double diag_add = b.add_diag ? S.P.noise + EXACT_INFERENCE_JITTER + (b.jitter ? b.jitter[slot] : 0.0) : 0.0;
+    const double diag_add = b.add_diag == 1 ? S.P.noise + EXACT_INFERENCE_JITTER + (b.jitter ? b.jitter[slot] : 0.0)
+                                             : (b.add_diag == 2 ? S.P.noise : 0.0);
     double* out = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB;
     double dsum = 0.0;
     // thread -> 64 elements: rows warp + 8k (k < 16), columns lane + 32m (m < 4): every warp store is one

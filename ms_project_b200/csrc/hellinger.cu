@@ -194,6 +194,110 @@ void launch_vector_pairs(const double* G, int S, int n, const int* pair_i, const
   g_launch_count++;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Subsets of more than 128 points (the reference hands the builders the WHOLE training set,
+// src/autoks/core/model_selection/smbo_model_selector.py:91-97): the Gram matrices are factorised by the blocked DMMA
+// Cholesky of the scoring path over the context's workspace slots instead of the one-CTA register factorisation.
+// ------------------------------------------------------------------------------------------------
+// logdet[item] = sum of the per-diagonal-block partials of the slot's factorisation
+__global__ void slot_logdet_kernel(Batch b, double* __restrict__ logdet, int* __restrict__ status) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= b.nslots) return;
+  const int item = b.ids[slot];
+  const bool bad = b.slot_status[slot] != 0;
+  double s = 0.0;
+  for (int k = 0; k < b.T; k++) s += b.logdet_part[slot * b.T + k];
+  logdet[item] = bad ? nan("") : s;
+  status[item] = bad ? 1 : 0;
+}
+
+void launch_slot_logdet(const Batch& b, double* logdet, int* status, cudaStream_t st) {
+  slot_logdet_kernel<<<(b.nslots + 127) / 128, 128, 0, st>>>(b, logdet, status);
+  g_launch_count++;
+}
+
+// M1[slot] (lower tiles) <- 1/2 (G_i,s + G_j,s) for work item w = w0 + slot: pair work_pair[w], sample work_s[w];
+// identity on the padding.  One CTA per 128 x 128 lower tile.
+__global__ void __launch_bounds__(256) havg_build_kernel(Batch b, const double* __restrict__ G, int S, int n,
+                                                         const int* __restrict__ pair_i, const int* __restrict__ pair_j,
+                                                         const int* __restrict__ work_pair, const int* __restrict__ work_s) {
+  const int slot = blockIdx.y;
+  int ti, tj;
+  tri_decode(blockIdx.x, ti, tj);
+  const int pr = work_pair[slot], s = work_s[slot];
+  const double* Gi = G + ((size_t)pair_i[pr] * S + s) * n * n;
+  const double* Gj = G + ((size_t)pair_j[pr] * S + s) * n * n;
+  double* out = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB;
+  const int c = threadIdx.x & (NB - 1), gj = tj * NB + c;
+  for (int r = threadIdx.x >> 7; r < NB; r += 2) {
+    const int gi = ti * NB + r;
+    double v = (gi == gj) ? 1.0 : 0.0;
+    if (gi < n && gj < n) v = 0.5 * (Gi[(size_t)gi * n + gj] + Gj[(size_t)gi * n + gj]);
+    out[(size_t)r * b.Np + c] = v;
+  }
+}
+
+void launch_havg_build(const Batch& b, const double* G, int S, int n, const int* pair_i, const int* pair_j,
+                       const int* work_pair, const int* work_s, cudaStream_t st) {
+  dim3 grid(tri_count(b.T), b.nslots);
+  havg_build_kernel<<<grid, 256, 0, st>>>(b, G, S, n, pair_i, pair_j, work_pair, work_s);
+  g_launch_count++;
+}
+
+// ldpq[pair][s] <- ld_i[s] (the value hellinger_distance keeps for samples it does not refactorise), hstatus <- 0
+__global__ void hpair_init_kernel(const double* __restrict__ logdet, int S, const int* __restrict__ pair_i, size_t total,
+                                  double* __restrict__ ldpq, int* __restrict__ hstatus) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+    const size_t pr = k / S;
+    ldpq[k] = logdet[(size_t)pair_i[pr] * S + (k % S)];
+    hstatus[k] = 0;
+  }
+}
+
+// scatter the chunk's log-determinants to their (pair, sample) cells
+__global__ void hpair_scatter_kernel(Batch b, int S, const int* __restrict__ work_pair, const int* __restrict__ work_s,
+                                     double* __restrict__ ldpq, int* __restrict__ hstatus) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= b.nslots) return;
+  const bool bad = b.slot_status[slot] != 0;
+  double s = 0.0;
+  for (int k = 0; k < b.T; k++) s += b.logdet_part[slot * b.T + k];
+  const size_t cell = (size_t)work_pair[slot] * S + work_s[slot];
+  ldpq[cell] = bad ? nan("") : s;
+  hstatus[cell] = bad ? 1 : 0;
+}
+
+// h[pair][s] = 1 - exp(1/4 (ld_i + ld_j) - 1/2 ldpq), in place over ldpq
+__global__ void hpair_combine_kernel(const double* __restrict__ logdet, int S, const int* __restrict__ pair_i,
+                                     const int* __restrict__ pair_j, size_t total, double* __restrict__ ldpq_h,
+                                     const int* __restrict__ hstatus) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+    const size_t pr = k / S;
+    const int s = (int)(k % S);
+    const double ldi = logdet[(size_t)pair_i[pr] * S + s], ldj = logdet[(size_t)pair_j[pr] * S + s];
+    ldpq_h[k] = hstatus[k] ? nan("") : 1.0 - exp(0.25 * (ldi + ldj) - 0.5 * ldpq_h[k]);
+  }
+}
+
+void launch_hpair_init(const double* logdet, int S, const int* pair_i, int npairs, double* ldpq, int* hstatus, cudaStream_t st) {
+  hpair_init_kernel<<<592, 256, 0, st>>>(logdet, S, pair_i, (size_t)npairs * S, ldpq, hstatus);
+  g_launch_count++;
+}
+
+void launch_hpair_scatter(const Batch& b, int S, const int* work_pair, const int* work_s, double* ldpq, int* hstatus,
+                          cudaStream_t st) {
+  hpair_scatter_kernel<<<(b.nslots + 127) / 128, 128, 0, st>>>(b, S, work_pair, work_s, ldpq, hstatus);
+  g_launch_count++;
+}
+
+void launch_hpair_finish(const double* logdet, int S, const int* pair_i, const int* pair_j, int npairs, double* ldpq_h,
+                         int* hstatus, double* dist, int* status, cudaStream_t st) {
+  hpair_combine_kernel<<<592, 256, 0, st>>>(logdet, S, pair_i, pair_j, (size_t)npairs * S, ldpq_h, hstatus);
+  hellinger_reduce_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(ldpq_h, hstatus, S, npairs, dist, status);
+  g_launch_count += 2;
+}
+
 int configure_hellinger_kernels() {
   cudaError_t e = cudaFuncSetAttribute(hellinger_precompute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(HellSmem));

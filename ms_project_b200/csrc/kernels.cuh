@@ -41,7 +41,8 @@ struct Batch {
   int* tries;                // [item] jitter-ladder tries used (may be null)
   int try_no;                // ladder step of this pipeline run (0 = plain)
   int quirks;
-  int add_diag;              // 1: add noise + 1e-8 + jitter to the diagonal (K_y); 0: bare kern.K
+  int add_diag;              // 1: add noise + 1e-8 + jitter to the diagonal (K_y); 2: add the noise only (Hellinger Gram
+                             // matrices K + lambda I, distance.py:186-190); 0: bare kern.K
   const double* lut;         // OP_LOOKUP distance matrix (lut_n x lut_n, b200gp_set_lookup) or null
   int lut_n;
   // compiled programs of this chunk (cprog.cuh), written by launch_compile

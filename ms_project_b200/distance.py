@@ -162,8 +162,10 @@ class HellingerDistanceBuilder(DistanceBuilder):
     def _init_device(self, data_X):
         torch = self.engine.torch
         n, D = data_X.shape
-        if n > 128:
-            raise NotImplementedError('the Hellinger subset must have at most 128 points (got %d)' % n)
+        # up to 128 points every Gram matrix is one CTA (in-register Cholesky, hellinger.cu); beyond that -- the reference
+        # hands the builders the whole training set (smbo_model_selector.py:91-97) -- the Gram matrices go through the
+        # scoring path's workspace slots (fused K-build + blocked DMMA Cholesky): b200gp_gram_logdet / _pairs_large
+        self._large = n > 128
         self._n, self._D = n, D
         self._X_host = np.ascontiguousarray(data_X)
         self._d_X = torch.from_numpy(self._X_host).to(self.engine.device)
@@ -197,9 +199,12 @@ class HellingerDistanceBuilder(DistanceBuilder):
         torch, eng = self.engine.torch, self.engine
         self._ensure_store(max(idx) + 1)
         kernels = [active_models.models[i].covariance.raw_kernel for i in idx]
-        batch = ProgramBatch(kernels)
         S = self.num_samples
         hyps = [prior_sample(get_priors(k), self.probability_samples) for k in kernels]        # each S x P_i
+        if self._large:
+            self._precompute_large(active_models, idx, kernels, hyps)
+            return
+        batch = ProgramBatch(kernels)
         theta_off = np.zeros(len(idx) + 1, dtype=np.int32)
         theta_off[1:] = np.cumsum([h.shape[1] for h in hyps])
         packed = np.concatenate([np.ascontiguousarray(h).reshape(-1) for h in hyps])
@@ -222,6 +227,57 @@ class HellingerDistanceBuilder(DistanceBuilder):
         ld_host, st_host = d_ld.cpu().numpy(), d_st.cpu().numpy()
         for j, i in enumerate(idx):
             active_models.models[i].info = HellingerInfo(self, i, ld_host[j].copy(), st_host[j].copy())
+
+    _needs_logdet = True        # the vector builders (Frobenius / correlation) only need the Gram matrices
+
+    def _precompute_large(self, active_models, idx, kernels, hyps):
+        """n > 128: one item per (model, sample), theta = [hyperparameter sample..., lambda_s], through the engine's
+        workspace slots (b200gp_gram_logdet, diag_mode 2 = K + lambda I)."""
+        torch, eng = self.engine.torch, self.engine
+        S, M, n = self.num_samples, len(idx), self._n
+        lam = np.asarray(self.hyperparameter_data_noise_samples[:, 0], dtype=np.float64)
+        batch = ProgramBatch([k for k in kernels for _ in range(S)])
+        eng.ensure_bound(self._X_host, np.zeros(n), batch.n_items, batch.max_params)
+        eng.upload_programs(batch)
+        theta = batch.pack_theta([hyps[m][s] for m in range(M) for s in range(S)], [lam[s] for _ in range(M) for s in range(S)])
+        d_G = torch.empty((M * S, n, n), dtype=torch.float64, device=eng.device)
+        d_ld = torch.full((M * S,), float('nan'), dtype=torch.float64, device=eng.device)
+        d_st = torch.zeros((M * S,), dtype=torch.int32, device=eng.device)
+        if self._needs_logdet:
+            eng.gram_logdet(batch, theta, 2, K_out=d_G, logdet=d_ld, status=d_st)
+        else:
+            eng.gram_logdet(batch, theta, 2, K_out=d_G)
+        sel = torch.tensor(idx, dtype=torch.long, device=eng.device)
+        self._d_logdet.index_copy_(0, sel, d_ld.view(M, S))
+        self._d_G.index_copy_(0, sel, d_G.view(M, S, n, n))
+        ld_host, st_host = d_ld.view(M, S).cpu().numpy(), d_st.view(M, S).cpu().numpy()
+        for j, i in enumerate(idx):
+            active_models.models[i].info = HellingerInfo(self, i, ld_host[j].copy(), st_host[j].copy())
+
+    def _pair_distances_large(self, pi, pj):
+        """n > 128: the host lists the (pair, sample) cells hellinger_distance refactorises (|ld_i - ld_j| > tol,
+        distance.py:145-153), the device factorises 1/2 (G_i + G_j) for exactly those in the workspace slots."""
+        torch, eng = self.engine.torch, self.engine
+        S = self.num_samples
+        ld = self._d_logdet.cpu().numpy()
+        with np.errstate(invalid='ignore'):
+            different = np.abs(ld[pi] - ld[pj]) > self.tol_logdet
+        wp, ws = np.nonzero(different)
+        nwork = int(wp.size)
+        eng.ensure_bound(self._X_host, np.zeros(self._n), max(nwork, 1), max(eng.max_params, 1))
+        d_pi, d_pj = torch.from_numpy(pi).to(eng.device), torch.from_numpy(pj).to(eng.device)
+        d_wp = torch.from_numpy(np.ascontiguousarray(wp, dtype=np.int32)).to(eng.device)
+        d_ws = torch.from_numpy(np.ascontiguousarray(ws, dtype=np.int32)).to(eng.device)
+        npairs = int(pi.size)
+        work = torch.empty(eng.lib.b200gp_hellinger_pairs_large_work_bytes(npairs, S), dtype=torch.uint8, device=eng.device)
+        d_dist = torch.empty(npairs, dtype=torch.float64, device=eng.device)
+        d_st = torch.empty(npairs, dtype=torch.int32, device=eng.device)
+        with eng.on_stream():
+            rc = eng.lib.b200gp_hellinger_pairs_large(eng.ctx, self._d_logdet.data_ptr(), self._d_G.data_ptr(), self._capacity, S,
+                                                      self._n, d_pi.data_ptr(), d_pj.data_ptr(), npairs, d_wp.data_ptr(),
+                                                      d_ws.data_ptr(), nwork, work.data_ptr(), d_dist.data_ptr(), d_st.data_ptr())
+            _lib.check(eng.ctx, rc, 'b200gp_hellinger_pairs_large')
+            return d_dist.cpu().numpy(), d_st.cpu().numpy()
 
     def create_precomputed_info(self, covariance, data_X):
         """distance.py:170-194 for one covariance -> (log_det[S], mini_gram[n, n, S]) host arrays."""
@@ -248,6 +304,8 @@ class HellingerDistanceBuilder(DistanceBuilder):
             return np.zeros(0), np.zeros(0, dtype=np.int32)
         if max(pi.max(), pj.max()) >= self._capacity:
             raise ValueError('pair refers to a model without precomputed information')
+        if self._large:
+            return self._pair_distances_large(pi, pj)
         d_pi, d_pj = torch.from_numpy(pi).to(eng.device), torch.from_numpy(pj).to(eng.device)
         S = self.num_samples
         work = torch.empty(eng.lib.b200gp_hellinger_pairs_work_bytes(npairs, S), dtype=torch.uint8, device=eng.device)
@@ -288,9 +346,25 @@ class HellingerDistanceBuilder(DistanceBuilder):
         Gj = np.ascontiguousarray(np.transpose(np.asarray(mini_gram_matrices_j, dtype=np.float64), (2, 0, 1)))
         S, n = Gi.shape[0], Gi.shape[1]
         d_G = torch.from_numpy(np.stack([Gi, Gj])).to(engine.device)
-        d_ld = torch.from_numpy(np.stack([np.asarray(log_det_i, dtype=np.float64), np.asarray(log_det_j, dtype=np.float64)])).to(engine.device)
+        ld2 = np.stack([np.asarray(log_det_i, dtype=np.float64), np.asarray(log_det_j, dtype=np.float64)])
+        d_ld = torch.from_numpy(ld2).to(engine.device)
         d_pi = torch.zeros(1, dtype=torch.int32, device=engine.device)
         d_pj = torch.ones(1, dtype=torch.int32, device=engine.device)
+        if n > 128:       # blocked path: only the order of the matrices matters for the binding
+            with np.errstate(invalid='ignore'):
+                ws = np.nonzero(np.abs(ld2[0] - ld2[1]) > tol)[0].astype(np.int32)
+            engine.bind(np.zeros((n, 1)), np.zeros(n), slots=max(int(ws.size), 1), max_params=1)
+            d_wp = torch.zeros(max(int(ws.size), 1), dtype=torch.int32, device=engine.device)
+            d_ws = torch.from_numpy(ws if ws.size else np.zeros(1, np.int32)).to(engine.device)
+            work = torch.empty(engine.lib.b200gp_hellinger_pairs_large_work_bytes(1, S), dtype=torch.uint8, device=engine.device)
+            d_dist = torch.empty(1, dtype=torch.float64, device=engine.device)
+            d_st = torch.empty(1, dtype=torch.int32, device=engine.device)
+            with engine.on_stream():
+                rc = engine.lib.b200gp_hellinger_pairs_large(engine.ctx, d_ld.data_ptr(), d_G.data_ptr(), 2, S, n, d_pi.data_ptr(),
+                                                             d_pj.data_ptr(), 1, d_wp.data_ptr(), d_ws.data_ptr(), int(ws.size),
+                                                             work.data_ptr(), d_dist.data_ptr(), d_st.data_ptr())
+                _lib.check(engine.ctx, rc, 'b200gp_hellinger_pairs_large')
+                return float(d_dist.cpu().numpy()[0])
         work = torch.empty(engine.lib.b200gp_hellinger_pairs_work_bytes(1, S), dtype=torch.uint8, device=engine.device)
         d_dist = torch.empty(1, dtype=torch.float64, device=engine.device)
         d_st = torch.empty(1, dtype=torch.int32, device=engine.device)
@@ -318,6 +392,7 @@ class _VectorDistanceBuilder(HellingerDistanceBuilder):
     """Shared machinery of FrobeniusDistanceBuilder / CorrelationDistanceBuilder (distance.py:197-284): the sampled prior
     Gram matrices are the ones the Hellinger precompute builds; only the pair metric differs."""
     _metric_code = 0
+    _needs_logdet = False
 
     def precompute_information(self, active_models, new_candidates_indices, data_X):
         super(_VectorDistanceBuilder, self).precompute_information(active_models, new_candidates_indices, data_X)

@@ -241,6 +241,18 @@ class Engine(object):
         _lib.check(self.ctx, rc, 'b200gp_build_K')
         return out.cpu().numpy()
 
+    def _gram_logdet_impl(self, batch, theta, diag_mode, K_out=None, logdet=None, status=None):
+        """Gram matrices (device tensor K_out [n_items, N, N]) and / or their log-determinants (device tensors) of every
+        item of an uploaded batch at the flat host `theta`; diag_mode as in b200gp_gram_logdet."""
+        batch.h_theta.numpy()[:] = theta
+        batch.d_theta.copy_(batch.h_theta, non_blocking=True)
+        rc = self.lib.b200gp_gram_logdet(self.ctx, batch.d_tokens.data_ptr(), batch.d_prog_off.data_ptr(), batch.d_theta.data_ptr(),
+                                         batch.d_theta_off.data_ptr(), batch.d_all_ids.data_ptr(), batch.n_items, int(diag_mode),
+                                         K_out.data_ptr() if K_out is not None else None,
+                                         logdet.data_ptr() if logdet is not None else None,
+                                         status.data_ptr() if status is not None else None)
+        _lib.check(self.ctx, rc, 'b200gp_gram_logdet')
+
     def _centered_alignments_impl(self, batch, theta):
         """Centred alignment of every pair of an uploaded batch's kernels over the bound X: n x n, diagonal 1."""
         torch = self.torch
@@ -295,6 +307,10 @@ class Engine(object):
     def build_K(self, *args, **kwargs):
         with self.on_stream():
             return self._build_K_impl(*args, **kwargs)
+
+    def gram_logdet(self, *args, **kwargs):
+        with self.on_stream():
+            return self._gram_logdet_impl(*args, **kwargs)
 
     def centered_alignments(self, *args, **kwargs):
         with self.on_stream():

@@ -107,3 +107,48 @@ def test_update_only_touches_requested_pairs():
     builder.update(am, new_candidates_indices=[5], all_candidates_indices=[3, 4, 5], selected_indices=[0, 1], data_X=x)
     assert not np.isnan(A[1, 3]) and not np.isnan(A[1, 4]) and not np.isnan(A[0, 5]) and not np.isnan(A[1, 5])
     assert np.isnan(A[0, 3])
+
+
+def test_large_subset_matches_oracle_and_small_path():
+    """More than 128 points (the reference hands the builders the whole training set, smbo_model_selector.py:91-97): Gram
+    matrices through the blocked DMMA Cholesky of the scoring path.  Parity against the oracle at n = 200, and the two
+    device paths against each other where both apply (n = 128 through the blocked entry points directly)."""
+    rng = np.random.default_rng(5)
+    x = rng.random((200, 2))
+    x = (x - x.mean(0)) / x.std(0)
+    am, builder, prob, noise_prior, pool = _setup(x, 12, 2, ['SE', 'RQ'], 2)
+    assert builder._large
+    infos, lam = _oracle_infos(pool, x, prob, noise_prior)
+    for m, (ld_ref, G_ref) in zip(am.models, infos):
+        ld, G = tuple(m.info)
+        assert np.all(m.info.status == 0)
+        assert G.shape == G_ref.shape == (200, 200, 20)
+        assert np.allclose(G, G_ref, rtol=1e-8, atol=1e-13)
+        assert np.allclose(ld, ld_ref, rtol=1e-9, atol=1e-8)
+    for i in range(len(pool)):
+        builder.compute_distance(am, [i], list(range(i + 1, len(pool))))
+    D = builder.get_kernel(len(pool))
+    D_ref = ohell.distance_matrix(infos)
+    off = ~np.eye(len(pool), dtype=bool)
+    assert np.allclose(D[off] ** 2, D_ref[off] ** 2, rtol=0, atol=1e-7), np.max(np.abs(D[off] ** 2 - D_ref[off] ** 2))
+    assert np.all(builder.last_status == 0)
+    d03 = builder.hellinger_distance(*tuple(am.models[0].info), *tuple(am.models[3].info))
+    assert abs(d03 ** 2 - D_ref[0, 3] ** 2) < 1e-7
+    # the same 128-point problem through both device paths
+    x2 = x[:128]
+    am_s, b_small, _, _, pool_s = _setup(x2, 8, 2, ['SE', 'RQ'], 2)
+    assert not b_small._large
+    for i in range(len(pool_s)):
+        b_small.compute_distance(am_s, [i], list(range(i + 1, len(pool_s))))
+    D_small = b_small.get_kernel(len(pool_s)).copy()
+    am_l, b_large, _, _, _ = _setup(x2, 8, 2, ['SE', 'RQ'], 2)
+    b_large._large = True                   # force the blocked path on the same subset
+    b_large.precompute_information(am_l, list(range(len(pool_s))), x2)
+    for ms, ml in zip(am_s.models, am_l.models):
+        assert np.allclose(tuple(ms.info)[0], tuple(ml.info)[0], rtol=1e-12, atol=1e-10)
+        assert np.allclose(tuple(ms.info)[1], tuple(ml.info)[1], rtol=1e-12, atol=1e-14)
+    for i in range(len(pool_s)):
+        b_large.compute_distance(am_l, [i], list(range(i + 1, len(pool_s))))
+    D_large = b_large.get_kernel(len(pool_s))
+    offs = ~np.eye(len(pool_s), dtype=bool)
+    assert np.allclose(D_small[offs] ** 2, D_large[offs] ** 2, rtol=0, atol=1e-10)

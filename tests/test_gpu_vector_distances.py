@@ -79,3 +79,28 @@ def test_pair_distances_match_oracle(which):
     assert abs(d05 - D_ref[0, 5]) <= 2e-3 * max(1.0, D_ref[0, 5])
     self_d, _ = builder.pair_distances([2], [2])
     assert abs(self_d[0]) < 1e-3
+
+
+def test_correlation_distance_on_more_than_128_points():
+    """The whole training set as the builders' data_X (n = 300): Gram matrices from b200gp_gram_logdet."""
+    from ms_project_b200.distance import CorrelationDistanceBuilder
+    rng = np.random.default_rng(4)
+    x = rng.random((300, 2))
+    x = (x - x.mean(0)) / x.std(0)
+    am, builder, prob, noise_prior, pool = _setup(CorrelationDistanceBuilder, x, 10, ['SE', 'RQ'], 2)
+    assert builder._large
+    lam = ohell.noise_samples(prior_tuple(noise_prior), prob)
+    vecs = []
+    for k, m in zip(pool, am.models):
+        kp = [prior_tuple(p.prior) for p in k.flattened_parameters()]
+        v_ref = ohell.create_vectors(to_oracle_expr(k), kp, x, prob, lam)
+        v = np.asarray(m.info)
+        assert v.shape == v_ref.shape == (300 * 300, 20)
+        assert np.allclose(v, v_ref, rtol=2e-6, atol=1e-7)
+        vecs.append(v_ref.astype(np.float64))
+    n = len(pool)
+    builder.compute_distance(am, list(range(n)), list(range(n)))
+    D = builder.get_kernel(n)
+    D64 = np.array([[ohell.correlation_distance(vecs[i], vecs[j]) for j in range(n)] for i in range(n)])
+    off = ~np.eye(n, dtype=bool)
+    assert np.allclose(D[off], D64[off], rtol=1e-9, atol=1e-7), np.max(np.abs(D[off] - D64[off]))

@@ -157,6 +157,55 @@ def c3(eng, budget):
                     'pairs_per_s': 1.0 / c_pair, 'projected_seconds_all_pairs': c_pair * ii.size + c_pre * n}}
 
 
+def c3full(eng, budget):
+    """The same BOMS Hellinger distance with the builders' data_X = the WHOLE C3 training set (n = 1024), which is what the
+    reference passes (smbo_model_selector.py:91-97): 100 candidates, 4950 pairs x 20 samples through the blocked path."""
+    import torch
+    from ms_project_b200 import workloads
+    from ms_project_b200.covariance import Covariance
+    from ms_project_b200.distance import ActiveModels, HellingerDistanceBuilder, probability_samples
+    from ms_project_b200.gpy_compat.priors import Gaussian
+    from oracle import hellinger as ohell
+    from oracle.adapter import to_oracle_expr, prior_tuple
+    X, Y, pool, _ = workloads.config_c3()
+    pool = pool[:100]
+    n, npts = len(pool), X.shape[0]
+    am = ActiveModels(max_n_models=n)
+    for k in pool:
+        am.add(_Model(Covariance(k)))
+    prob = probability_samples(40, 20)
+    noise_prior = Gaussian(np.log(0.01), 1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    builder = HellingerDistanceBuilder(noise_prior, 20, 40, n, am, list(range(n)), X, probability_samples_matrix=prob, engine=eng)
+    torch.cuda.synchronize()
+    t_pre = time.perf_counter() - t0
+    ii, jj = np.triu_indices(n, 1)
+    t0 = time.perf_counter()
+    dist, status = builder.pair_distances(ii, jj)
+    torch.cuda.synchronize()
+    t_pairs = time.perf_counter() - t0
+    ld = builder._d_logdet.cpu().numpy()
+    nwork = int((np.abs(ld[ii] - ld[jj]) > builder.tol_logdet).sum())
+    lam = ohell.noise_samples(prior_tuple(noise_prior), prob)
+    c0 = time.perf_counter()
+    infos = []
+    for k in pool[:2]:
+        kp = [prior_tuple(p.prior) for p in k.flattened_parameters()]
+        infos.append(ohell.create_precomputed_info(to_oracle_expr(k), kp, X, prob, lam))
+    c_pre = (time.perf_counter() - c0) / len(infos)
+    c0 = time.perf_counter()
+    d_ref = ohell.hellinger_distance(infos[0][0], infos[0][1], infos[1][0], infos[1][1])
+    c_pair = time.perf_counter() - c0
+    return {'config': 'C3 with data_X = the whole training set: 100 candidates, n=%d, D=4, S=20 (blocked DMMA path)' % npts,
+            'models': n, 'pairs': int(ii.size), 'precompute_seconds': t_pre, 'pairs_seconds': t_pairs,
+            'pair_sample_choleskys': nwork, 'fp64_tflops_pairs': nwork * (float(npts) ** 3 / 3.0) / t_pairs / 1e12,
+            'nan_distances': int(np.isnan(dist).sum()), 'bad_status': int((status != 0).sum()),
+            'parity_pair01_abs_err_d2': float(abs(dist[0] ** 2 - d_ref ** 2)),
+            'cpu': {'kind': 'port', 'precompute_seconds_per_model': c_pre, 'seconds_per_pair': c_pair,
+                    'projected_seconds_all_pairs': c_pair * ii.size + c_pre * n}}
+
+
 def c4(eng, budget):
     """evalg generation: 512 candidates, D = 8, N = 4096: one NLML+grad evaluation of the whole population."""
     import torch
@@ -278,7 +327,7 @@ def main():
     cores = host_cores()
     out = {'host_cores': cores}
     for name in args.configs.split(','):
-        fn = {'c1': c1, 'c3': c3, 'c4': c4, 'c5': c5}[name.strip()]
+        fn = {'c1': c1, 'c3': c3, 'c3full': c3full, 'c4': c4, 'c5': c5}[name.strip()]
         res = fn(eng, args.cpu_budget)
         out[name.strip()] = res
         print(json.dumps({name.strip(): res}))
