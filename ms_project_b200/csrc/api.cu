@@ -49,6 +49,10 @@ struct b200gp_ctx {
   bool panel_user = false;      // b200gp_set_panel_tiles was called: no adaptive choice
   int batch_panel_tiles = 8;    // batched Cholesky / L^-T (measured: 4 -> 26.6, 8 -> 26.2 ms per 256 items at N = 2048)
   bool fused_grad = false;      // K^-1 and the gradient of the <= 4-leaf programs in one kernel (kinv_grad_kernel)
+  int n_groups = 2;             // slot groups (streams) of the batched schedule (measured at 256 x N=2048: 1 group 89.2 ms,
+                                // 2 / 3 / 4 groups 87.8 ms -- the schedule is not the limiter)
+  cudaStream_t gstream[4]{};    // streams of the groups 1..3 (group 0 runs on the context stream)
+  cudaEvent_t gev[4]{};
   int la_slots = 65;            // batches below this many slots take the look-ahead / pipelined (latency) schedules
   double* ws_jitter = nullptr;
   int* ws_ids = nullptr;
@@ -160,6 +164,10 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
   cudaEventCreateWithFlags(&c->evR, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->evS, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->evI, cudaEventDisableTiming);
+  for (int q = 1; q < 4; q++) {
+    cudaStreamCreateWithFlags(&c->gstream[q], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->gev[q], cudaEventDisableTiming);
+  }
   *out = c;
   return 0;
 }
@@ -172,6 +180,7 @@ int b200gp_destroy(b200gp_ctx* c) {
   if (c->peer) cudaStreamDestroy(c->peer);
   if (c->evP) { cudaEventDestroy(c->evP); cudaEventDestroy(c->evR); cudaEventDestroy(c->evS); cudaEventDestroy(c->evI); }
   for (auto& e : c->evC) cudaEventDestroy(e);
+  for (int q = 1; q < 4; q++) { if (c->gstream[q]) cudaStreamDestroy(c->gstream[q]); if (c->gev[q]) cudaEventDestroy(c->gev[q]); }
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->h_ids) cudaFreeHost(c->h_ids);
   if (c->h_diag) cudaFreeHost(c->h_diag);
@@ -298,18 +307,16 @@ static void panel_schedule(b200gp_ctx* c, const Batch& b, PanelFn panel, UpdateF
   const bool la = (b.nslots < c->la_slots && T >= 2);
   if (!la) {
     const int W = c->batch_panel_tiles;
-    const bool split = b.nslots >= 16;
-    Batch g[2] = {b, b};
-    cudaStream_t st[2] = {c->stream, c->stream};
-    int ng = 1;
-    if (split) {
-      ng = 2;
-      g[0].nslots = b.nslots / 2;
-      g[1].slot0 = b.slot0 + g[0].nslots;
-      g[1].nslots = b.nslots - g[0].nslots;
-      st[1] = c->peer;
-      cudaEventRecord(c->evS, c->stream);
-      cudaStreamWaitEvent(c->peer, c->evS, 0);
+    const int ng = b.nslots >= 16 ? c->n_groups : 1;
+    Batch g[4] = {b, b, b, b};
+    cudaStream_t st[4] = {c->stream, c->gstream[1], c->gstream[2], c->gstream[3]};
+    if (ng > 1) cudaEventRecord(c->evS, c->stream);
+    int first = b.slot0;
+    for (int q = 0; q < ng; q++) {
+      g[q].slot0 = first;
+      g[q].nslots = (b.nslots * (q + 1)) / ng - (b.nslots * q) / ng;
+      first += g[q].nslots;
+      if (q > 0) cudaStreamWaitEvent(st[q], c->evS, 0);
     }
     for (int q = 0; q < ng; q++) {
       panel(g[q], 0, W < T ? W : T, st[q]);
@@ -319,9 +326,9 @@ static void panel_schedule(b200gp_ctx* c, const Batch& b, PanelFn panel, UpdateF
         panel(g[q], k1, (k1 + W < T) ? k1 + W : T, st[q]);
       }
     }
-    if (split) {
-      cudaEventRecord(c->evP, c->peer);
-      cudaStreamWaitEvent(c->stream, c->evP, 0);
+    for (int q = 1; q < ng; q++) {
+      cudaEventRecord(c->gev[q], st[q]);
+      cudaStreamWaitEvent(c->stream, c->gev[q], 0);
     }
     return;
   }
