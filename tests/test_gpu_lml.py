@@ -157,3 +157,58 @@ def test_fused_kinv_gradient_kernel_matches_oracle(engine):
         scale = max(1.0, np.max(np.abs(ref_g)))
         assert np.max(np.abs(dlml[a:b] - ref_g)) <= 1e-6 * scale, (KERNELS[i], dlml[a:b], ref_g)
         assert np.max(np.abs(dlml[a:b] - dlml2[a:b])) <= 1e-10 * scale
+
+
+@pytest.mark.parametrize('n', [1, 2, 127, 129, 255, 257])
+def test_tile_edge_sizes(engine, n):
+    """Orders around the 128-point tile edge (padding rows carry the identity) and the degenerate N = 1, 2."""
+    from ms_project_b200.program import ProgramBatch
+    from oracle import gp
+    rng = np.random.RandomState(n)
+    X = rng.randn(n, 2)
+    y = rng.randn(n, 1)
+    kernels = [from_string(s) for s in ['SE_1 + RQ_2', 'PER_1 * LIN_2 + CONST_1', 'SE_1 * SE_2']]
+    batch = ProgramBatch(kernels)
+    engine.bind(X, y, slots=2, max_params=batch.max_params)
+    engine.upload_programs(batch)
+    theta, ks, nz = random_theta(batch, np.random.RandomState(7))
+    lml, dlml, status, tries = engine.lml_grad(batch, theta)
+    for i, k in enumerate(kernels):
+        ref_lml, ref_g, _ = gp.lml_and_grad(to_oracle_expr(k), ks[i], nz[i], X, y)
+        a, b = batch.theta_off[i], batch.theta_off[i + 1]
+        assert status[i] == 0 and tries[i] == 0
+        assert abs(lml[i] - ref_lml) <= 1e-8 * max(1.0, abs(ref_lml)), (n, i, lml[i], ref_lml)
+        assert np.max(np.abs(dlml[a:b] - ref_g)) <= 1e-6 * max(1.0, np.max(np.abs(ref_g))), (n, i)
+
+
+def test_empty_batch_and_duplicate_inputs(engine):
+    """No items: nothing is launched, nothing is touched.  Repeated rows of X (collisions) make K singular; with the noise
+    term it stays positive definite and matches the oracle, without it the jitter ladder takes over like GPy's jitchol."""
+    from ms_project_b200.program import ProgramBatch
+    from oracle import gp
+    rng = np.random.RandomState(1)
+    X = np.repeat(rng.randn(50, 1), 3, axis=0)              # every point three times
+    y = rng.randn(150, 1)
+    kernels = [from_string('SE_1'), from_string('RQ_1 + LIN_1')]
+    batch = ProgramBatch(kernels)
+    engine.bind(X, y, slots=2, max_params=batch.max_params)
+    engine.upload_programs(batch)
+    theta, ks, nz = random_theta(batch, np.random.RandomState(3))
+    l0 = engine.launch_count()
+    out = engine.lml_grad(batch, theta, ids=np.zeros(0, dtype=np.int32))
+    assert engine.launch_count() == l0 and len(out) == 4
+    lml, dlml, status, tries = engine.lml_grad(batch, theta)
+    for i, k in enumerate(kernels):
+        ref_lml, ref_g, _ = gp.lml_and_grad(to_oracle_expr(k), ks[i], nz[i], X, y)
+        a, b = batch.theta_off[i], batch.theta_off[i + 1]
+        assert status[i] == 0
+        assert abs(lml[i] - ref_lml) <= 1e-8 * max(1.0, abs(ref_lml))
+        assert np.max(np.abs(dlml[a:b] - ref_g)) <= 1e-6 * max(1.0, np.max(np.abs(ref_g)))
+    # (almost) no noise: exactly repeated rows -> zero pivots -> jitchol ladder on both sides
+    nz0 = np.array([1e-300, 1e-300])
+    theta0 = batch.pack_theta(ks, nz0)
+    lml, dlml, status, tries = engine.lml_grad(batch, theta0)
+    for i, k in enumerate(kernels):
+        ref_lml, ref_g, inf = gp.lml_and_grad(to_oracle_expr(k), ks[i], nz0[i], X, y)
+        assert tries[i] >= 1 and status[i] == 1 and tries[i] == inf['tries'], (i, tries[i], inf['tries'])
+        assert abs(lml[i] - ref_lml) <= 1e-6 * max(1.0, abs(ref_lml)), (i, lml[i], ref_lml)
