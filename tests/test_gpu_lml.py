@@ -204,11 +204,12 @@ def test_empty_batch_and_duplicate_inputs(engine):
         assert status[i] == 0
         assert abs(lml[i] - ref_lml) <= 1e-8 * max(1.0, abs(ref_lml))
         assert np.max(np.abs(dlml[a:b] - ref_g)) <= 1e-6 * max(1.0, np.max(np.abs(ref_g)))
-    # (almost) no noise: exactly repeated rows -> zero pivots -> jitchol ladder on both sides
+    # (almost) no noise: exactly repeated rows leave only GPy's 1e-8 on the diagonal (condition number ~1e8); both sides must
+    # take the same number of jitchol rungs (none, if the 1e-8 is enough) and agree at the accuracy that conditioning allows
     nz0 = np.array([1e-300, 1e-300])
     theta0 = batch.pack_theta(ks, nz0)
     lml, dlml, status, tries = engine.lml_grad(batch, theta0)
     for i, k in enumerate(kernels):
         ref_lml, ref_g, inf = gp.lml_and_grad(to_oracle_expr(k), ks[i], nz0[i], X, y)
-        assert tries[i] >= 1 and status[i] == 1 and tries[i] == inf['tries'], (i, tries[i], inf['tries'])
+        assert tries[i] == inf['tries'] and status[i] == (1 if inf['tries'] else 0), (i, tries[i], inf['tries'])
         assert abs(lml[i] - ref_lml) <= 1e-6 * max(1.0, abs(ref_lml)), (i, lml[i], ref_lml)
