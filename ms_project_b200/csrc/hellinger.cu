@@ -70,7 +70,7 @@ hellinger_precompute_kernel(const double* __restrict__ Xsub, int n, int D, const
   for (int p = 0; p < TP_R; p++)
 #pragma unroll
     for (int q = 0; q < TP_R; q++) a[p][q] = Sm.stage[(ty + 16 * p) * (NB + 1) + tx + 16 * q];
-  tile_potrf<false>(a, Sm.T, n);
+  tile_potrf_pivots(a, Sm.T, n);
   const double ld = logdet_from_pivots(Sm.T, n);
   if (threadIdx.x == 0) {
     const bool bad = Sm.T.fail != 0;
@@ -104,7 +104,7 @@ hellinger_pair_kernel(const double* __restrict__ logdet, const double* __restric
         if (i < n && c < n) v = 0.5 * (Gi[(size_t)i * n + c] + Gj[(size_t)i * n + c]);
         a[p][q] = v;
       }
-    tile_potrf<false>(a, T, n);
+    tile_potrf_pivots(a, T, n);
     ldpq = logdet_from_pivots(T, n);
     bad = T.fail != 0;
   }
