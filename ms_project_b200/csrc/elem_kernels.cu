@@ -28,6 +28,9 @@
 #ifndef POLY_GRAD_CTAS
 #define POLY_GRAD_CTAS 2
 #endif
+#ifndef POLY_GRAD8_CTAS
+#define POLY_GRAD8_CTAS 2      // 5-8 leaf gradient kernel: 128 registers with ~300 B of spills beats 212 registers at one CTA per SM (C4: 56 -> 38 ms)
+#endif
 #ifndef POLY_E8
 #define POLY_E8 1
 #endif
@@ -376,7 +379,7 @@ __device__ __forceinline__ unsigned term_mask(unsigned terms4, unsigned term_add
 }
 
 template <int LMAX, int E>
-__global__ void __launch_bounds__(256, LMAX == 4 ? POLY_BUILD_CTAS : 1) poly_build_kernel(Batch b, int kind) {
+__global__ void __launch_bounds__(256, LMAX == 4 ? POLY_BUILD_CTAS : 2) poly_build_kernel(Batch b, int kind) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef PolySmem<LMAX> SM;
   SM& S = *reinterpret_cast<SM*>(smem_raw);
@@ -555,7 +558,7 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
 constexpr int GP_PER_TILE = 2;
 
 template <int LMAX, int E>
-__global__ void __launch_bounds__(256, LMAX == 4 ? POLY_GRAD_CTAS : 1) poly_grad_kernel(Batch b, int kind) {
+__global__ void __launch_bounds__(256, LMAX == 4 ? POLY_GRAD_CTAS : POLY_GRAD8_CTAS) poly_grad_kernel(Batch b, int kind) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef PolySmem<LMAX> SM;
   SM& S = *reinterpret_cast<SM*>(smem_raw);
