@@ -20,7 +20,7 @@
 
 // rows a thread of the polynomial-form kernels interleaves (independent FP64 chains)
 #ifndef POLY_E4
-#define POLY_E4 2
+#define POLY_E4 4              // <= 4-leaf build kernel: 4 rows per step halve the per-step op dispatch (4.7 -> 4.3 ms / 256 items)
 #endif
 #ifndef POLY_BUILD_CTAS
 #define POLY_BUILD_CTAS 3      // resident CTAs per SM the <= 4-leaf kernels are compiled for (register cap 85: 78 used, no spills; 5.7 -> 5.1 ms per 256 items)
@@ -35,7 +35,7 @@
 #define POLY_E8 1
 #endif
 #ifndef POLY_GE4
-#define POLY_GE4 POLY_E4       // rows interleaved by the gradient kernels (kept apart from the build kernel's for tuning)
+#define POLY_GE4 2             // rows interleaved by the <= 4-leaf gradient kernel (4 would spill at 128 registers)
 #endif
 
 namespace b200gp {
