@@ -219,6 +219,9 @@ int main(int argc, char** argv) {
   std::vector<double> chk;
   run<4, 2, 3, 16, 2, 1>("skew 4x2 S3 KC16 x2", M, C, ld, slots, Ks, &chk);
   run<4, 2, 3, 16, 2, 2>("skew+pred 4x2 S3 KC16 x2", M, C, ld, slots, Ks, &chk);
+  run<4, 2, 2, 32, 2, 1>("skew 4x2 S2 KC32 x2", M, C, ld, slots, Ks, &chk);
+  run<4, 2, 2, 32, 2, 2>("skew+pred 4x2 S2 KC32 x2", M, C, ld, slots, Ks, &chk);
+  run<4, 2, 5, 8, 2, 1>("skew 4x2 S5 KC8 x2", M, C, ld, slots, Ks, &chk);
   return 0;
   run<4, 4, 4, 16, 1, 0>("base 4x4 S4 KC16", M, C, ld, slots, Ks, &chk);
   run<4, 4, 4, 16, 1, 1>("skew 4x4 S4 KC16", M, C, ld, slots, Ks, &chk);
