@@ -32,6 +32,9 @@ def test_misuse_is_reported_not_executed():
         assert lib.b200gp_build_K(ctx, ip, ip, p, ip, ip, 1, 0, p) != 0
         assert lib.b200gp_posterior(ctx, ip, ip, p, ip, ip, 0, p, 4, 1, p, p, p, ip) != 0
         assert lib.b200gp_centered_alignments(ctx, ip, ip, p, ip, ip, 2, p) != 0
+        assert lib.b200gp_gram_logdet(ctx, ip, ip, p, ip, ip, 1, 2, p, p, ip) != 0
+        assert lib.b200gp_hellinger_pairs_large(ctx, p, p, 2, 4, 40, ip, ip, 1, ip, ip, 1, p, p, ip) != 0
+        assert b'b200gp_bind' in lib.b200gp_last_error(ctx)
         # bind: geometry and workspace checks
         X, y = make_data(40, 2, seed=0)
         dX, dy = torch.from_numpy(X).to(dev), torch.from_numpy(y.reshape(-1)).to(dev)
@@ -51,6 +54,12 @@ def test_misuse_is_reported_not_executed():
         assert lib.b200gp_posterior(ctx, ip, ip, p, ip, ip, 0, p, 0, 1, p, p, p, ip) != 0   # Ns = 0
         assert lib.b200gp_centered_alignments(ctx, ip, ip, p, ip, ip, 3, p) != 0            # 3 kernels, 2 slots
         assert b'slots' in lib.b200gp_last_error(ctx)
+        assert lib.b200gp_gram_logdet(ctx, ip, ip, p, ip, ip, 1, 3, p, p, ip) != 0            # unknown diag_mode
+        assert lib.b200gp_gram_logdet(ctx, ip, ip, p, ip, ip, 1, 2, None, p, None) != 0       # log-determinants without a status buffer
+        assert lib.b200gp_gram_logdet(ctx, ip, ip, p, ip, ip, 1, 2, None, None, None) == 0    # nothing asked for: no-op
+        assert lib.b200gp_hellinger_pairs_large(ctx, p, p, 2, 4, 64, ip, ip, 1, ip, ip, 1, p, p, ip) != 0   # bound to 40 points, not 64
+        assert b'bound to 40 points' in lib.b200gp_last_error(ctx)
+        assert lib.b200gp_hellinger_pairs_large_work_bytes(0, 4) == 0 and lib.b200gp_hellinger_pairs_large_work_bytes(3, 4) > 0
         # standalone entry points
         assert lib.b200gp_vector_pairs(ctx, p, 2, 4, 3, ip, ip, 1, 7, p) != 0               # unknown metric
         assert lib.b200gp_hellinger_precompute(ctx, p, 129, 2, ip, ip, p, ip, p, 1, 4, p, None, ip) != 0   # subset > 128
