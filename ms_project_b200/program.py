@@ -120,7 +120,12 @@ class ProgramBatch(object):
 
     def __init__(self, kernels):
         self.kernels = list(kernels)
-        progs = [compile_kernel(k) for k in self.kernels]
+        compiled = {}                    # the same kernel object repeated (restarts, prior samples) is compiled once
+        progs = []
+        for k in self.kernels:
+            if id(k) not in compiled:
+                compiled[id(k)] = compile_kernel(k)
+            progs.append(compiled[id(k)])
         self.n_items = len(progs)
         self.n_params = np.array([p for _, p in progs], dtype=np.int64)      # kernel params (noise excluded)
         self.tokens = np.concatenate([t for t, _ in progs], axis=0) if progs else np.zeros((0, 4), np.int32)
@@ -132,8 +137,11 @@ class ProgramBatch(object):
         self.max_dim = int(max((t[_leaf_rows(t), 1].max() for t, _ in progs), default=0))
         # OP_LOOKUP leaves (BOMS surrogate): every such leaf of a batch reads ONE distance table, the builder's
         self.lookup = None
+        seen = set()
         for k in self.kernels:
-            k.traverse(self._note_lookup)
+            if id(k) not in seen:
+                seen.add(id(k))
+                k.traverse(self._note_lookup)
 
     def _note_lookup(self, k):
         if getattr(k, 'op_name', None) == 'LOOKUP':
