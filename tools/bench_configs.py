@@ -47,21 +47,25 @@ def c1(eng, budget):
                 seen.add(key)
                 out.append(k)
         return out
-    np.random.seed(0)
-    ev = BatchedEvaluator(fitness.negative_bic, n_restarts_optimizer=3, engine=eng,
-                          model_dict=gp_regression(likelihood_hyperprior={'variance': noise_prior}))
-    cands = [GPModel(Covariance(k.copy())) for k in bases]
+    def search():
+        np.random.seed(0)
+        ev = BatchedEvaluator(fitness.negative_bic, n_restarts_optimizer=3, engine=eng,
+                              model_dict=gp_regression(likelihood_hyperprior={'variance': noise_prior}))
+        cands = [GPModel(Covariance(k.copy())) for k in bases]
+        seq, n_scored, evals = [], 0, 0
+        t0 = time.perf_counter()
+        for d in range(3):
+            done = ev.evaluate_models(cands, X, Y, eval_budget=10 ** 6)
+            n_scored += len(done)
+            evals += sum(m.fit_result.n_evals for m in done)
+            best = max((m for m in cands if m.evaluated), key=lambda m: m.score)
+            seq.append(program.infix_string(best.covariance.raw_kernel))
+            cands = [GPModel(Covariance(k)) for k in expand(best.covariance.raw_kernel)]
+        return seq, n_scored, evals, time.perf_counter() - t0
+
     first = [k.copy() for k in bases]
-    seq, n_scored, evals = [], 0, 0
-    t0 = time.perf_counter()
-    for d in range(3):
-        done = ev.evaluate_models(cands, X, Y, eval_budget=10 ** 6)
-        n_scored += len(done)
-        evals += sum(m.fit_result.n_evals for m in done)
-        best = max((m for m in cands if m.evaluated), key=lambda m: m.score)
-        seq.append(program.infix_string(best.covariance.raw_kernel))
-        cands = [GPModel(Covariance(k)) for k in expand(best.covariance.raw_kernel)]
-    dt = time.perf_counter() - t0
+    _, _, _, dt_cold = search()           # first search of the process: second engine / workspaces are created inside it
+    seq, n_scored, evals, dt = search()   # the timed one (same seed, same result)
     # CPU: the same first-level candidates, sequentially, until the budget is spent
     rng = np.random.RandomState(0)
     c0, n_cpu, cpu_evals = time.perf_counter(), 0, 0
@@ -75,7 +79,7 @@ def c1(eng, budget):
             break
     cdt = time.perf_counter() - c0
     return {'config': 'C1 CKS depth 3, SE/RQ/LIN/PER, N=500, 3 restarts, nBIC', 'selected_sequence': seq,
-            'candidates_fitted': n_scored, 'nlml_grad_evaluations': int(evals), 'seconds': dt,
+            'candidates_fitted': n_scored, 'nlml_grad_evaluations': int(evals), 'seconds': dt, 'seconds_first_search_of_process': dt_cold,
             'candidates_per_s': n_scored / dt, 'evaluations_per_s': evals / dt,
             'cpu': {'kind': 'port', 'candidates': n_cpu, 'seconds': cdt, 'candidates_per_s': n_cpu / cdt,
                     'evaluations_per_s': cpu_evals / cdt if cpu_evals else None}}
