@@ -1,6 +1,7 @@
 // C-ABI of libb200gp (include/b200gp.h): context, workspace carving, phase orchestration, jitter ladder.
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -48,6 +49,8 @@ struct b200gp_ctx {
   int panel_tiles = 4;          // look-ahead Cholesky (single large matrix)
   bool panel_user = false;      // b200gp_set_panel_tiles was called: no adaptive choice
   int batch_panel_tiles = 8;    // batched Cholesky / L^-T (measured: 4 -> 26.6, 8 -> 26.2 ms per 256 items at N = 2048)
+  int gemm64 = 1;               // Cholesky / L^-T updates on 64 x 64 CTA tiles
+  bool kinv64 = true;           // K^-1 on 64 x 64 CTA tiles with CTA-granular skipping (kinv64_kernel) instead of kinv_kernel
   bool fused_grad = false;      // K^-1 and the gradient of the <= 4-leaf programs in one kernel (kinv_grad_kernel)
   int n_groups = 2;             // slot groups (streams) of the batched schedule (measured at 256 x N=2048: 1 group 89.2 ms,
                                 // 2 / 3 / 4 groups 87.8 ms -- the schedule is not the limiter)
@@ -168,6 +171,8 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
     cudaStreamCreateWithFlags(&c->gstream[q], cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&c->gev[q], cudaEventDisableTiming);
   }
+  if (const char* e = getenv("B200GP_KINV64")) c->kinv64 = atoi(e) != 0;       // tuning aid
+  if (const char* e = getenv("B200GP_GEMM64")) c->gemm64 = atoi(e);            // tuning aid
   *out = c;
   return 0;
 }
@@ -258,6 +263,7 @@ int b200gp_bind(b200gp_ctx* c, void* ws, size_t ws_bytes, int slots, int max_par
   b.M1 = l.M1; b.M2 = l.M2; b.Dinv = l.Dinv; b.z = l.z; b.alpha = l.alpha;
   b.logdet_part = l.logdet_part; b.diag_part = l.diag_part; b.grad_part = l.grad_part; b.solve_part = l.solve_part;
   b.pstride = max_params + 1;
+  b.gemm64 = c->gemm64;
   b.slot_status = l.slot_status;
   b.Xt = l.Xt; b.y = l.y;
   b.cprog = l.cprog; b.klist = l.klist; b.kcount = l.kcount; b.list_stride = slots;
@@ -442,7 +448,9 @@ static void run_pipeline(b200gp_ctx* c, const Batch& b, int with_grad) {
   launch_solve(b, s);
   if (prof) cudaEventRecord(c->ev[4], s);
   if (with_grad) {
-    if (c->fused_grad) launch_kinv_grad(b, s); else launch_gemm(b, GM_KINV, 0, s);
+    if (c->fused_grad) launch_kinv_grad(b, s);
+    else if (c->kinv64) launch_kinv64(b, s);
+    else launch_gemm(b, GM_KINV, 0, s);
   }
   if (prof) cudaEventRecord(c->ev[5], s);
   if (with_grad) launch_grad(b, s, c->fused_grad);
@@ -616,6 +624,7 @@ int b200gp_potrf(b200gp_ctx* c, double* dA, int N, void* work, double* logdet, i
   Batch b{};
   b.N = N; b.Np = N; b.T = T; b.D = 0; b.nslots = 1; b.mstride = (size_t)N * N;
   b.M1 = dA; b.M2 = nullptr;
+  b.gemm64 = c->gemm64;
   b.Dinv = cv.take<double>((size_t)T * NB * NB);
   b.logdet_part = cv.take<double>(T);
   b.slot_status = cv.take<int>(1);

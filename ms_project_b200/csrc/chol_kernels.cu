@@ -115,6 +115,194 @@ __global__ void __launch_bounds__(TG_THREADS, 2) kinv_kernel(Batch b) {
   gemm_body<GM_KINV>(b, 0, UpdRange{0, 0, 0, 0}, blockIdx.x >> 1, blockIdx.x & 1);
 }
 
+// ------------------------------------------------------------------------------------------------
+// K^-1 = V V^T on 64 x 64 CTA tiles.
+//
+// tools/gemm_probe ("kinv pattern") compares CTA tile shapes on exactly this phase's work: tile lengths from K = 64 to N in
+// one launch, upper-triangular first K block, only the lower triangle wanted.  Skipping the structural zeros per WARP inside
+// 128 x 64 tiles (kinv_kernel) saves 16 % of the flops but costs as much pipe efficiency, because the skipping warps wait
+// at the chunk barrier for the working ones: 29.9 TF/s in the probe, the same as not skipping at all (29.6).  Skipping
+// per CTA at 64 x 64 granularity -- blocks above the diagonal are not launched, block row I starts at k = 64 I -- removes
+// half of that waste with no predicate in the inner loop: 32.3 TF/s in the probe with 3 CTAs (4 warps each) per SM.
+// Every output element still sums its products in ascending k, so the values are bit-identical to kinv_kernel's.
+// ------------------------------------------------------------------------------------------------
+constexpr int K64_T = 64;                                  // CTA tile edge
+constexpr int K64_THREADS = 128;                           // 2 x 2 warps of 32 x 32
+constexpr int K64_STAGE_DOUBLES = 2 * K64_T * TG_LDK;      // A (64 rows) + B (64 rows), 16 k each
+constexpr int K64_SMEM_BYTES = TG_STAGES * K64_STAGE_DOUBLES * 8;     // 61,440 B -> three CTAs per SM
+
+// acc (this warp's 32 x 32 part of the 64 x 64 block) += A(64 x 16 nchunks) B(64 x 16 nchunks)^T, both operands row-major with
+// K contiguous from the given pointers: the skewed pipeline of tile_gemm.cuh (barrier in front of a chunk's last k-step,
+// next fragments fetched behind it) on a 3-stage ring of 64 + 64 rows, no predicate anywhere.
+__device__ __forceinline__ void tile64_pipeline(double (&acc)[TG_MT][TG_NT][2], const double* __restrict__ A,
+                                                const double* __restrict__ B, size_t ld, int nchunks, double* smem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int g = lane >> 2, tg = lane & 3;
+  const int aoff = (wm * 32 + g) * TG_LDK + tg;
+  const int boff = (K64_T + wn * 32 + g) * TG_LDK + tg;
+  auto load = [&](int stage, int chunk) {
+    double* st = smem + stage * K64_STAGE_DOUBLES;
+#pragma unroll
+    for (int r = 0; r < 2 * K64_T * 8 / K64_THREADS; r++) {
+      const int seg = threadIdx.x + K64_THREADS * r;        // 8 16-byte segments per row, rows 0..63 = A, 64..127 = B
+      const int row = seg >> 3, part = (seg & 7) * 2;
+      const double* src = (row < K64_T ? A + (size_t)row * ld : B + (size_t)(row - K64_T) * ld) + chunk * TG_KC + part;
+      cp_async16(st + row * TG_LDK + part, src);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < TG_STAGES - 1; s++) {
+    if (s < nchunks) load(s, s);
+    cp_async_commit();
+  }
+  cp_async_wait<TG_STAGES - 2>();
+  __syncthreads();
+  double a[TG_MT], bf[TG_NT];
+#pragma unroll
+  for (int mt = 0; mt < TG_MT; mt++) a[mt] = smem[aoff + mt * 8 * TG_LDK];
+#pragma unroll
+  for (int nt = 0; nt < TG_NT; nt++) bf[nt] = smem[boff + nt * 8 * TG_LDK];
+  for (int kc = 0; kc < nchunks; kc++) {
+    {
+      const int nk = kc + TG_STAGES - 1;
+      if (nk < nchunks) load(nk % TG_STAGES, nk);
+      cp_async_commit();
+    }
+    const double* As = smem + (kc % TG_STAGES) * K64_STAGE_DOUBLES + aoff;
+    const double* Bs = smem + (kc % TG_STAGES) * K64_STAGE_DOUBLES + boff;
+    const double* An = smem + ((kc + 1) % TG_STAGES) * K64_STAGE_DOUBLES + aoff;
+    const double* Bn = smem + ((kc + 1) % TG_STAGES) * K64_STAGE_DOUBLES + boff;
+#pragma unroll
+    for (int kk = 0; kk < TG_KC; kk += 4) {
+      double a2[TG_MT], b2[TG_NT];
+      if (kk + 4 < TG_KC) {
+#pragma unroll
+        for (int mt = 0; mt < TG_MT; mt++) a2[mt] = As[mt * 8 * TG_LDK + kk + 4];
+#pragma unroll
+        for (int nt = 0; nt < TG_NT; nt++) b2[nt] = Bs[nt * 8 * TG_LDK + kk + 4];
+      } else {
+        cp_async_wait<TG_STAGES - 2>();
+        __syncthreads();
+#pragma unroll
+        for (int mt = 0; mt < TG_MT; mt++) a2[mt] = An[mt * 8 * TG_LDK];
+#pragma unroll
+        for (int nt = 0; nt < TG_NT; nt++) b2[nt] = Bn[nt * 8 * TG_LDK];
+      }
+#pragma unroll
+      for (int mt = 0; mt < TG_MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < TG_NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], bf[nt]);
+#pragma unroll
+      for (int mt = 0; mt < TG_MT; mt++) a[mt] = a2[mt];
+#pragma unroll
+      for (int nt = 0; nt < TG_NT; nt++) bf[nt] = b2[nt];
+    }
+  }
+  cp_async_wait<0>();
+}
+
+// this thread's first element of the 64 x 64 block at C (fragment layout of tile_gemm.cuh on 2 x 2 warps)
+__device__ __forceinline__ double* tile64_cw(double* C, size_t ld) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  return C + (size_t)((warp >> 1) * 32 + (lane >> 2)) * ld + (warp & 1) * 32 + (lane & 3) * 2;
+}
+
+// acc <- beta C (beta = 0: zeros, C not read)
+__device__ __forceinline__ void tile64_init(double (&acc)[TG_MT][TG_NT][2], const double* Cw, size_t ld, double beta) {
+#pragma unroll
+  for (int mt = 0; mt < TG_MT; mt++)
+#pragma unroll
+    for (int nt = 0; nt < TG_NT; nt++) {
+      double2 v = make_double2(0.0, 0.0);
+      if (beta != 0.0) v = *reinterpret_cast<const double2*>(Cw + (size_t)(mt * 8) * ld + nt * 8);
+      acc[mt][nt][0] = beta * v.x;
+      acc[mt][nt][1] = beta * v.y;
+    }
+}
+
+__device__ __forceinline__ void tile64_store(const double (&acc)[TG_MT][TG_NT][2], double* Cw, size_t ld, double alpha) {
+#pragma unroll
+  for (int mt = 0; mt < TG_MT; mt++)
+#pragma unroll
+    for (int nt = 0; nt < TG_NT; nt++)
+      *reinterpret_cast<double2*>(Cw + (size_t)(mt * 8) * ld + nt * 8) = make_double2(alpha * acc[mt][nt][0], alpha * acc[mt][nt][1]);
+}
+
+__global__ void __launch_bounds__(K64_THREADS, 3) kinv64_kernel(Batch b) {
+  const int slot = b.slot0 + blockIdx.y;
+  if (b.slot_status[slot] != 0) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int I, J;
+  tri_decode(blockIdx.x, I, J);                            // block row ascending = K length descending
+  const size_t ld = b.Np;
+  const double* V = b.M2 + slot * b.mstride;
+  double acc[TG_MT][TG_NT][2];
+  tile64_init(acc, nullptr, ld, 0.0);
+  tile64_pipeline(acc, V + (size_t)(I * K64_T) * ld + I * K64_T, V + (size_t)(J * K64_T) * ld + I * K64_T, ld,
+                  (b.Np - I * K64_T) / TG_KC, reinterpret_cast<double*>(smem_raw));
+  tile64_store(acc, tile64_cw(b.M1 + slot * b.mstride + (size_t)(I * K64_T) * ld + J * K64_T, ld), ld, 1.0);
+}
+
+// Cholesky trailing / in-panel update on 64 x 64 blocks: A_ij -= sum_{k in [k0, k0+kw)} L_ik L_jk^T.  blockIdx.x = 4 x (tile
+// index of chol_update_kernel) + quadrant; the upper-right quadrant of a diagonal tile is never read and does no work.
+__global__ void __launch_bounds__(K64_THREADS, 3) chol_update64_kernel(Batch b, UpdRange upd) {
+  const int slot = b.slot0 + blockIdx.y;
+  if (b.slot_status[slot] != 0) return;
+  const int bx = blockIdx.x >> 2, vi = (blockIdx.x >> 1) & 1, vj = blockIdx.x & 1;
+  int i, j;
+  if (upd.j1 >= b.T) {
+    int r, c;
+    tri_decode(bx, r, c);
+    i = upd.j0 + r; j = upd.j0 + c;
+  } else {
+    int rem = bx;
+    j = upd.j0;
+    while (rem >= b.T - j) { rem -= b.T - j; j++; }
+    i = j + rem;
+  }
+  if (i == j && vj > vi) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t ld = b.Np;
+  double* M1 = b.M1 + slot * b.mstride;
+  const int ri = i * NB + vi * K64_T, rj = j * NB + vj * K64_T;
+  double* Cw = tile64_cw(M1 + (size_t)ri * ld + rj, ld);
+  double acc[TG_MT][TG_NT][2];
+  tile64_init(acc, Cw, ld, -1.0);                          // accumulators start at -C: the C read overlaps the pipeline fill
+  tile64_pipeline(acc, M1 + (size_t)ri * ld + upd.k0 * NB, M1 + (size_t)rj * ld + upd.k0 * NB, ld, upd.kw * (NB / TG_KC),
+                  reinterpret_cast<double*>(smem_raw));
+  tile64_store(acc, Cw, ld, -1.0);
+}
+
+// Right-looking L^-T update on 64 x 64 blocks: S_jm (+)= sum_{i in [max(j,k0), k0+kw)} V_ji L_mi^T.  When the K range starts at
+// V_jj (upper triangular) the lower 64 rows of the tile skip its first 64 columns.
+__global__ void __launch_bounds__(K64_THREADS, 3) inv_update64_kernel(Batch b, UpdRange upd) {
+  const int slot = b.slot0 + blockIdx.y;
+  if (b.slot_status[slot] != 0) return;
+  const int bx = blockIdx.x >> 2, vi = (blockIdx.x >> 1) & 1, vj = blockIdx.x & 1;
+  const int J = upd.k0 + upd.kw;
+  const int m = upd.j0 + bx / J, j = bx % J;
+  const int kb = j > upd.k0 ? j : upd.k0;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t ld = b.Np;
+  double* M1 = b.M1 + slot * b.mstride;
+  double* M2 = b.M2 + slot * b.mstride;
+  const int rj = j * NB + vi * K64_T, rm = m * NB + vj * K64_T;
+  const int kskip = (kb == j && vi == 1) ? K64_T : 0;      // structural zeros of V_jj below its diagonal
+  double* Cw = tile64_cw(M2 + (size_t)rj * ld + rm, ld);
+  double acc[TG_MT][TG_NT][2];
+  tile64_init(acc, Cw, ld, (j >= upd.k0) ? 0.0 : 1.0);
+  tile64_pipeline(acc, M2 + (size_t)rj * ld + kb * NB + kskip, M1 + (size_t)rm * ld + kb * NB + kskip, ld,
+                  ((J - kb) * NB - kskip) / TG_KC, reinterpret_cast<double*>(smem_raw));
+  tile64_store(acc, Cw, ld, 1.0);
+}
+
+void launch_kinv64(const Batch& b, cudaStream_t s) {
+  dim3 grid(tri_count(2 * b.T), b.nslots);
+  kinv64_kernel<<<grid, K64_THREADS, K64_SMEM_BYTES, s>>>(b);
+  g_launch_count++;
+}
+
 void launch_gemm(const Batch& b, int mode, int step, cudaStream_t s) {
   int ntiles = 0;
   switch (mode) {
@@ -143,8 +331,13 @@ void launch_vupdate(const Batch& b, UpdRange r, cudaStream_t s) {
   const int j1 = r.j1 < b.T ? r.j1 : b.T;
   const int ntiles = (j1 - r.j0) * (r.k0 + r.kw);
   if (ntiles <= 0 || r.kw <= 0) return;
-  dim3 grid(2 * ntiles, b.nslots);
-  inv_update_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, r);
+  if (b.gemm64) {
+    dim3 grid(4 * ntiles, b.nslots);
+    inv_update64_kernel<<<grid, K64_THREADS, K64_SMEM_BYTES, s>>>(b, r);
+  } else {
+    dim3 grid(2 * ntiles, b.nslots);
+    inv_update_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, r);
+  }
   g_launch_count++;
 }
 
@@ -152,8 +345,13 @@ void launch_update(const Batch& b, UpdRange r, cudaStream_t s) {
   int ntiles = 0;
   for (int j = r.j0; j < r.j1 && j < b.T; j++) ntiles += b.T - j;
   if (ntiles <= 0 || r.kw <= 0) return;
-  dim3 grid(2 * ntiles, b.nslots);
-  chol_update_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, r);
+  if (b.gemm64) {
+    dim3 grid(4 * ntiles, b.nslots);
+    chol_update64_kernel<<<grid, K64_THREADS, K64_SMEM_BYTES, s>>>(b, r);
+  } else {
+    dim3 grid(2 * ntiles, b.nslots);
+    chol_update_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, r);
+  }
   g_launch_count++;
 }
 
@@ -243,6 +441,11 @@ int configure_chol_kernels() {
                          (const void*)inv_update_kernel, (const void*)kinv_kernel};
   for (const void* f : gemms) {
     e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const void* g64[] = {(const void*)kinv64_kernel, (const void*)chol_update64_kernel, (const void*)inv_update64_kernel};
+  for (const void* f : g64) {
+    e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, K64_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
   }
   return 0;

@@ -45,6 +45,7 @@ struct Batch {
                              // matrices K + lambda I, distance.py:186-190); 0: bare kern.K
   const double* lut;         // OP_LOOKUP distance matrix (lut_n x lut_n, b200gp_set_lookup) or null
   int lut_n;
+  int gemm64;                // 1: Cholesky / L^-T updates on 64 x 64 CTA tiles (chol_update64 / inv_update64), 0: 128 x 64 tiles
   // compiled programs of this chunk (cprog.cuh), written by launch_compile
   CProg* cprog;              // [slot]
   int* klist;                // [CK_KINDS][list_stride] slots of each kind, in slot order
@@ -64,6 +65,7 @@ void launch_build_k(const Batch& b, cudaStream_t s);
 void launch_export_sym(const Batch& b, double* out, cudaStream_t s);       // out[slot][N][N] symmetric copy of M1
 void launch_potrf_diag(const Batch& b, int k, cudaStream_t s);
 void launch_gemm(const Batch& b, int mode, int step, cudaStream_t s);
+void launch_kinv64(const Batch& b, cudaStream_t s);                        // K^-1 = V V^T on 64 x 64 CTA tiles (same values as GM_KINV)
 void launch_update(const Batch& b, UpdRange r, cudaStream_t s);
 void launch_vupdate(const Batch& b, UpdRange r, cudaStream_t s);
 void launch_solve(const Batch& b, cudaStream_t s);                          // z = L^-1 y, alpha = L^-T z

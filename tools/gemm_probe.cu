@@ -21,21 +21,55 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <int WM, int WN, int STAGES, int KC, int MINB, int SKEW>
+// PATTERN 1 emulates kinv_kernel (K^-1 = V V^T, V upper triangular): blockIdx.x walks the (TM x TN) blocks on or below
+// the diagonal of the ld x ld output (longest K first), block row ti only needs k >= ti TM, the first TM columns of its A
+// operand are upper triangular (row m needs k >= m: per-warp kc_lo) and warp tiles strictly above the diagonal are
+// skipped (kc_hi = 0); the per-warp range is applied with the runtime predicate of SKEW = 2.
+template <int WM, int WN, int STAGES, int KC, int MINB, int SKEW, int PATTERN = 0>
 __global__ void __launch_bounds__(32 * WM * WN, MINB)
 gemm_variant(const double* __restrict__ M, double* __restrict__ Cout, int ld, int K, int tiles_m, int tiles_n, int kc_lo, int kc_hi) {
   constexpr int TM = 32 * WM, TN = 32 * WN, NT = 32 * WM * WN, LDK = KC + 4;
   constexpr int STAGE = (TM + TN) * LDK;
   extern __shared__ __align__(16) double smem[];
   const int slot = blockIdx.y;
-  const int ti = blockIdx.x / tiles_n, tj = blockIdx.x % tiles_n;
-  const double* A = M + (size_t)slot * ld * ld + (size_t)(ti * TM) * ld;
-  const double* B = M + (size_t)slot * ld * ld + (size_t)(tj * TN) * ld;
-  double* C = Cout + (size_t)slot * ld * ld + (size_t)(ti * TM) * ld + tj * TN;
+  int ti = blockIdx.x / tiles_n, tj = blockIdx.x % tiles_n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = warp / WN, wn = (warp - wm) % WN;
   const int g = lane >> 2, tg = lane & 3;
-  const int nchunks = K / KC;
+  int nchunks = K / KC;
+  int kbase = 0;
+  if (PATTERN == 1) {
+    // enumerate blocks (ti, tj) with tj TN < (ti + 1) TM, block rows in ascending order (= descending K length)
+    int rem = blockIdx.x;
+    ti = 0;
+    while (true) {
+      const int cnt = ((ti + 1) * TM + TN - 1) / TN;
+      if (rem < cnt) break;
+      rem -= cnt;
+      ti++;
+    }
+    tj = rem;
+    kbase = ti * TM;
+    nchunks = (ld - kbase) / KC;
+    kc_lo = (wm * 32) / KC;
+    kc_hi = (tj * TN + wn * 32 >= ti * TM + wm * 32 + 32) ? 0 : nchunks;
+  }
+  if (PATTERN == 2) {      // same enumeration, skipping at CTA granularity only (no per-warp predicate: use SKEW = 1)
+    int rem = blockIdx.x;
+    ti = 0;
+    while (true) {
+      const int cnt = ((ti + 1) * TM + TN - 1) / TN;
+      if (rem < cnt) break;
+      rem -= cnt;
+      ti++;
+    }
+    tj = rem;
+    kbase = ti * TM;
+    nchunks = (ld - kbase) / KC;
+  }
+  const double* A = M + (size_t)slot * ld * ld + (size_t)(ti * TM) * ld + kbase;
+  const double* B = M + (size_t)slot * ld * ld + (size_t)(tj * TN) * ld + kbase;
+  double* C = Cout + (size_t)slot * ld * ld + (size_t)(ti * TM) * ld + tj * TN;
 
   auto load_stage = [&](int s, int koff) {
     double* As = smem + s * STAGE;
@@ -199,6 +233,36 @@ void run(const char* name, const double* M, double* C, int ld, int slots, const 
   if (check) check->push_back(s);
 }
 
+template <int WM, int WN, int STAGES, int KC, int MINB, int PATTERN = 1>
+void run_kinv(const char* name, const double* M, double* C, int ld, int slots) {
+  constexpr int TM = 32 * WM, TN = 32 * WN;
+  const int smem = STAGES * (TM + TN) * (KC + 4) * 8;
+  auto fn = gemm_variant<WM, WN, STAGES, KC, MINB, PATTERN == 1 ? 2 : 1, PATTERN>;
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * WM * WN, smem));
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, fn));
+  int nblk = 0;
+  for (int ti = 0; ti < ld / TM; ti++) nblk += ((ti + 1) * TM + TN - 1) / TN;
+  dim3 grid(nblk, slots);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  fn<<<grid, 32 * WM * WN, smem>>>(M, C, ld, ld, ld / TM, ld / TN, 0, 0);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  const int reps = 3;
+  CK(cudaEventRecord(e0));
+  for (int r = 0; r < reps; r++) fn<<<grid, 32 * WM * WN, smem>>>(M, C, ld, ld, ld / TM, ld / TN, 0, 0);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  const double tf = (double)ld * ld * ld / 3.0 * slots * reps / (ms * 1e-3) / 1e12;
+  printf("kinv pattern %-22s tile %3dx%3d thr %3d smem %6d regs %3d CTAs/SM %d blocks/slot %4d | %6.2f TF/s algorithmic (N^3/3), %.3f ms per slot\n",
+         name, TM, TN, 32 * WM * WN, smem, fa.numRegs, per_sm, nblk, tf, ms / reps / slots);
+}
+
 __global__ void fill(double* p, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     unsigned long long x = i * 6364136223846793005ull + 1442695040888963407ull;
@@ -217,6 +281,21 @@ int main(int argc, char** argv) {
   CK(cudaDeviceSynchronize());
   std::vector<int> Ks = {128, 512, 2048};
   std::vector<double> chk;
+  if (argc > 2) {      // kinv-pattern comparison of CTA tile shapes
+    run_kinv<4, 2, 3, 16, 2>("4x2 S3 x2 (library)", M, C, ld, slots);
+    run_kinv<2, 2, 3, 16, 3>("2x2 S3 x3", M, C, ld, slots);
+    run_kinv<2, 2, 2, 16, 4>("2x2 S2 x4", M, C, ld, slots);
+    run_kinv<2, 4, 3, 16, 2>("2x4 S3 x2", M, C, ld, slots);
+    run_kinv<4, 4, 3, 16, 1>("4x4 S3 x1", M, C, ld, slots);
+    run_kinv<2, 1, 4, 16, 6>("2x1 S4 x6", M, C, ld, slots);
+    printf("CTA-granular skipping only (no per-warp predicate):\n");
+    run_kinv<4, 2, 3, 16, 2, 2>("4x2 S3 x2", M, C, ld, slots);
+    run_kinv<2, 2, 3, 16, 3, 2>("2x2 S3 x3", M, C, ld, slots);
+    run_kinv<2, 2, 2, 16, 4, 2>("2x2 S2 x4", M, C, ld, slots);
+    run_kinv<1, 2, 4, 16, 6, 2>("1x2 S4 x6", M, C, ld, slots);
+    run_kinv<1, 1, 4, 16, 8, 2>("1x1 S4 x8", M, C, ld, slots);
+    return 0;
+  }
   run<4, 2, 3, 16, 2, 1>("skew 4x2 S3 KC16 x2", M, C, ld, slots, Ks, &chk);
   run<4, 2, 3, 16, 2, 2>("skew+pred 4x2 S3 KC16 x2", M, C, ld, slots, Ks, &chk);
   run<4, 2, 2, 32, 2, 1>("skew 4x2 S2 KC32 x2", M, C, ld, slots, Ks, &chk);
