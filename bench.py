@@ -255,7 +255,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
 
-    # ---- roofline of the dominant kernel: kinv_kernel (one launch per step: K^-1 = V V^T on the DMMA pipe,
+    # ---- roofline of the dominant kernel: kinv64_kernel (one launch per step: K^-1 = V V^T on the DMMA pipe,
     #      N^3/3 flops per item), timed by the library's CUDA events around that launch in every timed step ----
     phases = (phase_sum / max(args.steps, 1)).tolist()
     chunk_items = n_items - ((n_items + slots - 1) // slots - 1) * slots     # items of the (last) chunk the events cover
@@ -266,9 +266,9 @@ def run_ours(args, rank, world, local_rank):
     traffic, traffic_note = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic_r01.json')))
-        per_item = (tr['kinv_kernel']['dram_bytes_read'] + tr['kinv_kernel']['dram_bytes_write']) / tr['items_per_launch']
+        per_item = (tr['kinv64_kernel']['dram_bytes_read'] + tr['kinv64_kernel']['dram_bytes_write']) / tr['items_per_launch']
         traffic = per_item * chunk_items
-        traffic_note = ('dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of kinv_kernel at %d items per '
+        traffic_note = ('dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of kinv64_kernel at %d items per '
                         'launch, scaled to the %d items of this launch (algorithmic: 8 N^2 bytes per item = read V upper + '
                         'write K^-1 lower)' % (tr['items_per_launch'], chunk_items))
     except Exception:
@@ -292,11 +292,11 @@ def run_ours(args, rank, world, local_rank):
             'clocks': sampler.summary(),
             'roofline': {'bound': 'tensor', 'achieved': kinv_tflops, 'peak': peak, 'unit': 'TFLOP/s', 'frac': kinv_tflops / peak,
                          'traffic': traffic, 'traffic_note': traffic_note, 'algorithmic_bytes': 8.0 * N_DATA ** 2 * chunk_items,
-                         'kernel': 'kinv_kernel (FP64 DMMA tile GEMM, K^-1 = V V^T; 1 launch per step)',
+                         'kernel': 'kinv64_kernel (FP64 DMMA tile GEMM on 64 x 64 CTA tiles, K^-1 = V V^T; 1 launch per step)',
                          'algorithmic': 'N^3/3 flops per item x %d items per launch' % chunk_items,
                          'launch_ms': phases[4], 'peak_source': peak_src},
             'roofline_dmma_phases': {'achieved': dmma_tflops, 'peak': peak, 'unit': 'TFLOP/s', 'frac': dmma_tflops / peak,
-                                     'kernels': 'chol_update/chol_trsm/potrf_diag + inv_update/inv_trsm + kinv (Cholesky, L^-T, K^-1)',
+                                     'kernels': 'chol_update64/chol_trsm/potrf_diag + inv_update64/inv_trsm + kinv64 (Cholesky, L^-T, K^-1)',
                                      'algorithmic': 'N^3 flops per item', 'ms': dmma_ms},
             'phases_ms': {'build_K': phases[0], 'cholesky': phases[1], 'inverse': phases[2], 'solve': phases[3],
                           'Kinv': phases[4], 'grad': phases[5], 'items': chunk_items},

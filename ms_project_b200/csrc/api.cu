@@ -1,7 +1,6 @@
 // C-ABI of libb200gp (include/b200gp.h): context, workspace carving, phase orchestration, jitter ladder.
 #include <cmath>
 #include <cstdarg>
-#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -171,8 +170,6 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
     cudaStreamCreateWithFlags(&c->gstream[q], cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&c->gev[q], cudaEventDisableTiming);
   }
-  if (const char* e = getenv("B200GP_KINV64")) c->kinv64 = atoi(e) != 0;       // tuning aid
-  if (const char* e = getenv("B200GP_GEMM64")) c->gemm64 = atoi(e);            // tuning aid
   *out = c;
   return 0;
 }

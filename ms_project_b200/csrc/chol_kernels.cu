@@ -135,7 +135,9 @@ constexpr int K64_SMEM_BYTES = TG_STAGES * K64_STAGE_DOUBLES * 8;     // 61,440 
 // K contiguous from the given pointers: the skewed pipeline of tile_gemm.cuh (barrier in front of a chunk's last k-step,
 // next fragments fetched behind it) on a 3-stage ring of 64 + 64 rows, no predicate anywhere.
 __device__ __forceinline__ void tile64_pipeline(double (&acc)[TG_MT][TG_NT][2], const double* __restrict__ A,
-                                                const double* __restrict__ B, size_t ld, int nchunks, double* smem) {
+                                                const double* __restrict__ B, size_t ld, int nchunks, double* smem,
+                                                size_t ldb = 0) {
+  if (ldb == 0) ldb = ld;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = warp >> 1, wn = warp & 1;
   const int g = lane >> 2, tg = lane & 3;
@@ -147,7 +149,7 @@ __device__ __forceinline__ void tile64_pipeline(double (&acc)[TG_MT][TG_NT][2], 
     for (int r = 0; r < 2 * K64_T * 8 / K64_THREADS; r++) {
       const int seg = threadIdx.x + K64_THREADS * r;        // 8 16-byte segments per row, rows 0..63 = A, 64..127 = B
       const int row = seg >> 3, part = (seg & 7) * 2;
-      const double* src = (row < K64_T ? A + (size_t)row * ld : B + (size_t)(row - K64_T) * ld) + chunk * TG_KC + part;
+      const double* src = (row < K64_T ? A + (size_t)row * ld : B + (size_t)(row - K64_T) * ldb) + chunk * TG_KC + part;
       cp_async16(st + row * TG_LDK + part, src);
     }
   };
@@ -297,6 +299,32 @@ __global__ void __launch_bounds__(K64_THREADS, 3) inv_update64_kernel(Batch b, U
   tile64_store(acc, Cw, ld, 1.0);
 }
 
+// In-place triangular solves on 64 x 64 blocks: X D^T with D the 128 x 128 inverse of a diagonal block of L (lower
+// triangular, so output columns [64 vj, 64 vj + 64) need k < 64 (vj + 1)).  A CTA owns 64 rows of one tile: the right block
+// first (it reads all 128 columns and writes columns 64..127), then the left one.
+//   VT = false: L_ik = A_ik D_k^T          (Cholesky, tile rows i > step of M1)
+//   VT = true:  V_ji = -S_ji D_i^T         (L^-T, tile rows j < step of M2)
+template <bool VT>
+__global__ void __launch_bounds__(K64_THREADS, 3) trsm64_kernel(Batch b, int step) {
+  const int slot = b.slot0 + blockIdx.y;
+  if (b.slot_status[slot] != 0) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* smem = reinterpret_cast<double*>(smem_raw);
+  const int t = blockIdx.x >> 1, vi = blockIdx.x & 1;
+  const int row_tile = VT ? t : step + 1 + t;
+  const size_t ld = b.Np;
+  double* X = (VT ? b.M2 : b.M1) + slot * b.mstride + (size_t)(row_tile * NB + vi * K64_T) * ld + step * NB;
+  const double* D = b.Dinv + ((size_t)slot * b.T + step) * (NB * NB);
+  double acc[TG_MT][TG_NT][2];
+#pragma unroll
+  for (int vj = 1; vj >= 0; vj--) {
+    tile64_init(acc, nullptr, ld, 0.0);
+    tile64_pipeline(acc, X, D + (size_t)(vj * K64_T) * NB, ld, (vj + 1) * (K64_T / TG_KC), smem, NB);
+    tile64_store(acc, tile64_cw(X + vj * K64_T, ld), ld, VT ? -1.0 : 1.0);
+    __syncthreads();      // every warp has left the stages (and stored its part) before the left block refills them
+  }
+}
+
 void launch_kinv64(const Batch& b, cudaStream_t s) {
   dim3 grid(tri_count(2 * b.T), b.nslots);
   kinv64_kernel<<<grid, K64_THREADS, K64_SMEM_BYTES, s>>>(b);
@@ -313,11 +341,15 @@ void launch_gemm(const Batch& b, int mode, int step, cudaStream_t s) {
   if (ntiles <= 0) return;
   dim3 grid(ntiles, b.nslots);
   switch (mode) {
+    // the 64 x 64 form doubles the CTAs of these small launches: one N = 2048 evaluation 1.8 -> 1.6 ms; on large batches the
+    // two forms are equal (25.0 vs 24.9 ms per 256 items), so it is used below 65 slots (and always with gemm64 = 2)
     case GM_TRSM:
-      chol_trsm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, step);
+      if (b.gemm64 >= 2 || (b.gemm64 == 1 && b.nslots < 65)) { grid.x *= 2; trsm64_kernel<false><<<grid, K64_THREADS, K64_SMEM_BYTES, s>>>(b, step); }
+      else chol_trsm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, step);
       break;
     case GM_VTRSM:
-      inv_trsm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, step);
+      if (b.gemm64 >= 2 || (b.gemm64 == 1 && b.nslots < 65)) { grid.x *= 2; trsm64_kernel<true><<<grid, K64_THREADS, K64_SMEM_BYTES, s>>>(b, step); }
+      else inv_trsm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, step);
       break;
     default:
       grid.x *= 2;
@@ -443,7 +475,8 @@ int configure_chol_kernels() {
     e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
   }
-  const void* g64[] = {(const void*)kinv64_kernel, (const void*)chol_update64_kernel, (const void*)inv_update64_kernel};
+  const void* g64[] = {(const void*)kinv64_kernel, (const void*)chol_update64_kernel, (const void*)inv_update64_kernel,
+                       (const void*)trsm64_kernel<false>, (const void*)trsm64_kernel<true>};
   for (const void* f : g64) {
     e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, K64_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;

@@ -15,9 +15,9 @@ $PROBE > $O/probe_plain_$TAG.log 2>&1 || exit 1
 cap() {  # name, kernel regex, skip
   ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o $O/prof_$1_$TAG $PROBE > $O/ncu_$1_$TAG.log 2>&1
 }
-cap upd chol_update_kernel 3      # 4th launch = the K = 512 trailing update of the first panel (slot group 0)
-cap vupd inv_update_kernel 3
-cap kinv kinv_kernel 0
+cap upd chol_update64_kernel 3    # 4th launch of the Cholesky update kernel
+cap vupd inv_update64_kernel 3
+cap kinv kinv64_kernel 0
 cap trsm chol_trsm_kernel 2
 cap grad poly_grad_kernel 0
 cap build poly_build_kernel 0

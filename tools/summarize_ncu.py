@@ -90,6 +90,7 @@ def launches(tag):
         out.append('| `%s` | %d | %.2f | %.1f%% |' % (k, n, ns / 1e6, 100 * ns / total))
     out.append('| **all** | %d | %.2f | 100%% |' % (sum(a[0] for a in agg.values()), total / 1e6))
     dm = sum(ns for k, (n, ns) in agg.items() if k in ('chol_update_kernel', 'inv_update_kernel', 'kinv_kernel',
+                                                     'chol_update64_kernel', 'inv_update64_kernel', 'kinv64_kernel',
                                                      'chol_trsm_kernel', 'inv_trsm_kernel', 'gemm_kernel'))
     out += ['', 'DMMA tile-GEMM kernels together: %.1f%% of the kernel time.' % (100 * dm / total)]
     shutil.copy(path, os.path.join(PROF, 'launches_%s.csv' % tag))
