@@ -165,6 +165,10 @@ int b200gp_set_profiling(b200gp_ctx* ctx, int enabled);
 /* panel width (in 128-column tiles) of the blocked Cholesky / L^-T schedules; the default is chosen per batch
  * (1-2 tile columns for latency-bound small batches, 4 for a single large matrix, 8 for large batches) */
 int b200gp_set_panel_tiles(b200gp_ctx* ctx, int tiles);
+/* CTA tile shape of the DMMA phases.  1 (default): 64 x 64 tiles, three 4-warp CTAs per SM, structural zeros skipped per
+ * CTA; 0: 128 x 64 tiles, two 8-warp CTAs per SM, structural zeros skipped per warp.  The results are bit-identical
+ * (tests/test_gpu_fullsize.py); the 64 x 64 form is 3-5 % faster on every phase. */
+int b200gp_set_tile64(b200gp_ctx* ctx, int enabled);
 /* 1: K^-1 and the gradient pass of the <= 4-leaf programs run as ONE kernel (K^-1 never reaches HBM); 0 (default): two
  * kernels.  Same results up to the order of the partial sums; measured +0.8 % throughput at N = 2048. */
 int b200gp_set_fused_grad(b200gp_ctx* ctx, int enabled);

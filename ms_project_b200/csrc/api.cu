@@ -215,6 +215,14 @@ int b200gp_set_panel_tiles(b200gp_ctx* c, int tiles) {
   return 0;
 }
 
+int b200gp_set_tile64(b200gp_ctx* c, int enabled) {
+  if (!c) return -1;
+  c->gemm64 = enabled ? 1 : 0;
+  c->kinv64 = enabled != 0;
+  c->base.gemm64 = c->gemm64;
+  return 0;
+}
+
 int b200gp_set_fused_grad(b200gp_ctx* c, int enabled) {
   if (!c) return -1;
   c->fused_grad = enabled != 0;

@@ -69,6 +69,10 @@ class Engine(object):
     def set_panel_tiles(self, tiles):
         _lib.check(self.ctx, self.lib.b200gp_set_panel_tiles(self.ctx, int(tiles)), 'b200gp_set_panel_tiles')
 
+    def set_tile64(self, on):
+        """CTA tile shape of the DMMA phases: 64 x 64 (default) or 128 x 64; bit-identical results."""
+        _lib.check(self.ctx, self.lib.b200gp_set_tile64(self.ctx, int(bool(on))), 'b200gp_set_tile64')
+
     def set_fused_grad(self, on):
         """K^-1 fused with the gradient pass of the <= 4-leaf programs (one kernel, K^-1 never written to HBM)."""
         _lib.check(self.ctx, self.lib.b200gp_set_fused_grad(self.ctx, int(bool(on))), 'b200gp_set_fused_grad')

@@ -39,6 +39,15 @@ def test_c2_size_parity_and_schedule_independence(engine):
     a, b = batch.theta_off[33], batch.theta_off[34]
     assert lml1[33] == lml80[33] and lml20[33] == lml80[33]
     assert np.array_equal(g1[a:b], g80[a:b]) and np.array_equal(g20[a:b], g80[a:b])
+    # the 128 x 64 CTA tiles (per-warp skipping of the structural zeros) give the same bits as the default 64 x 64 tiles
+    engine.set_tile64(False)
+    try:
+        lml_w, g_w, st_w, _ = [a_.copy() for a_ in engine.lml_grad(batch, theta)]
+        lml_w1, g_w1, _, _ = [a_.copy() for a_ in engine.lml_grad(batch, theta, ids=np.array([33], dtype=np.int32))]
+    finally:
+        engine.set_tile64(True)
+    assert (st_w == 0).all() and np.array_equal(lml_w, lml80) and np.array_equal(g_w, g80)
+    assert lml_w1[33] == lml80[33] and np.array_equal(g_w1[a:b], g80[a:b])
 
 
 def test_c5_size_cholesky_and_gradient_properties(engine):
