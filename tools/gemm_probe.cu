@@ -294,6 +294,10 @@ int main(int argc, char** argv) {
     run_kinv<2, 2, 2, 16, 4, 2>("2x2 S2 x4", M, C, ld, slots);
     run_kinv<1, 2, 4, 16, 6, 2>("1x2 S4 x6", M, C, ld, slots);
     run_kinv<1, 1, 4, 16, 8, 2>("1x1 S4 x8", M, C, ld, slots);
+    run_kinv<2, 2, 2, 32, 3, 2>("2x2 S2 KC32 x3", M, C, ld, slots);
+    run_kinv<2, 2, 4, 8, 3, 2>("2x2 S4 KC8 x3", M, C, ld, slots);
+    run_kinv<2, 2, 5, 8, 4, 2>("2x2 S5 KC8 x4", M, C, ld, slots);
+    run_kinv<2, 2, 3, 16, 2, 2>("2x2 S3 x2", M, C, ld, slots);
     return 0;
   }
   run<4, 2, 3, 16, 2, 1>("skew 4x2 S3 KC16 x2", M, C, ld, slots, Ks, &chk);
