@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     l = _lib.lib()
     for name in sorted(declared):
         assert hasattr(l, name), 'libb200gp.so does not export %s' % name
-    assert set(_lib.EXPORTS) <= declared
+    assert set(_lib.EXPORTS) == declared          # the ctypes binding covers the whole header
     assert b'sm_100a' in l.b200gp_version()
 
 
