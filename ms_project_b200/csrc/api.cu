@@ -124,7 +124,7 @@ Layout carve(void* ws, int N, int D, int slots, int max_params) {
   l.alpha = c.take<double>(S * Np);
   l.logdet_part = c.take<double>(S * T);
   l.diag_part = c.take<double>(S * T);
-  l.grad_part = c.take<double>(S * tri_count(T) * 2 * (size_t)(max_params + 1));
+  l.grad_part = c.take<double>(S * tri_count(T) * 4 * (size_t)(max_params + 1));
   l.solve_part = c.take<double>(S * tri_count(T) * (size_t)NB);
   l.Xt = c.take<double>((size_t)D * Np);
   l.y = c.take<double>(Np);

@@ -13,6 +13,7 @@
 // costs one wave of CTAs that exit at once.
 #include "kernels.cuh"
 #include "gemm_body.cuh"
+#include "tile_gemm64.cuh"
 #include "kprog.cuh"
 #include "cprog.cuh"
 #include "fastmath.cuh"
@@ -445,22 +446,27 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? POLY_BUILD_CTAS : 2) poly_bui
   }
 }
 
-// Gradient contribution of the COLS columns [col0, col0 + COLS) of tile (ti, tj).  Thread (c, h) = (tid % COLS, tid / COLS)
-// owns column col0 + c and the rows [h RPH, (h + 1) RPH), RPH = 128 COLS / 256.  `Kt` points at (row 0, column col0) of the
-// K^-1 tile, `kld` is its row stride: global memory (Np) for the stand-alone kernel, the staged copy in shared memory for
-// the fused K^-1 + gradient kernel.  `out`: this work item's entry of grad_part.
-template <int LMAX, int E, int COLS>
+// Gradient contribution of the ROWS x COLS block of tile (ti, tj) whose first element is (rbase, col0), by a CTA of THREADS
+// threads.  Thread (c, h) = (tid % COLS, tid / COLS) owns column col0 + c and the rows [rbase + h RPH, rbase + (h + 1) RPH),
+// RPH = ROWS COLS / THREADS.  `Kt` points at (row 0 of the TILE, column col0) of K^-1, `kld` is its row stride: global memory
+// (Np) for the stand-alone kernel, the staged copy in shared memory for the fused K^-1 + gradient kernels.  `out`: this work
+// item's entry of grad_part.
+template <int LMAX, int E, int COLS, int THREADS = 256, int ROWS = NB>
 __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, const Batch& b, int slot, int ti, int tj, int col0,
-                                               const double* Kt, size_t kld, double* out) {
+                                               const double* Kt, size_t kld, double* out, int rbase = 0) {
   typedef PolySmem<LMAX> SM;
   constexpr int NV = 3 * LMAX + 1;
-  constexpr int RPH = NB * COLS / 256;
+  constexpr int RPH = ROWS * COLS / THREADS;
   const int c = threadIdx.x % COLS, h = threadIdx.x / COLS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double Aj[LMAX], Sj[LMAX], Cj[LMAX];
   int ops[LMAX];
   poly_prologue<LMAX>(S, b, slot, ti, tj, col0 + c, Aj, Sj, Cj, ops);
-  if (threadIdx.x >= NB) S.ai[threadIdx.x - NB] = b.alpha[(size_t)slot * b.Np + ti * NB + threadIdx.x - NB];
+  if (THREADS >= 2 * NB) {
+    if (threadIdx.x >= NB && threadIdx.x < 2 * NB) S.ai[threadIdx.x - NB] = b.alpha[(size_t)slot * b.Np + ti * NB + threadIdx.x - NB];
+  } else {
+    for (int r = threadIdx.x; r < NB; r += THREADS) S.ai[r] = b.alpha[(size_t)slot * b.Np + ti * NB + r];
+  }
   const double aj = b.alpha[(size_t)slot * b.Np + tj * NB + col0 + c];
   __syncthreads();
   const int L = S.cp.L, G = S.cp.G, single = S.cp.single;
@@ -471,9 +477,9 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
   const double* Kinv = Kt + c;
   const int gj = tj * NB + col0 + c;
   // diagonal tiles: rows above this warp's first column hold no lower-triangle element
-  int rbeg = h * RPH;
+  int rbeg = rbase + h * RPH;
   if (ti == tj) { const int cmin = col0 + c - lane; if (cmin > rbeg) rbeg = cmin / E * E; }
-  const int rend = h * RPH + RPH;
+  const int rend = rbase + h * RPH + RPH;
   double kv[E];
 #pragma unroll
   for (int e = 0; e < E; e++) kv[e] = (rbeg < rend) ? Kinv[(size_t)(rbeg + e) * kld] : 0.0;
@@ -543,7 +549,7 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
     const int i = threadIdx.x;
     double s = 0.0;
 #pragma unroll
-    for (int q = 0; q < 8; q++) s += S.red[q][i];
+    for (int q = 0; q < THREADS / 32; q++) s += S.red[q][i];
     if (i == NV - 1) out[S.cp.nparam] = s;
     else {
       const int l = i / 3, p = i % 3;
@@ -553,9 +559,10 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
   }
 }
 
-// grad_part holds GP_PER_TILE entries per (slot, tile): the fused kernel writes one per 128 x 64 half tile, the
-// stand-alone kernels fill entry 0 and clear entry 1; finalize_kernel sums all of them in index order.
-constexpr int GP_PER_TILE = 2;
+// grad_part holds GP_PER_TILE entries per (slot, tile): the fused kernels write one per 64 x 64 quadrant (or per 128 x 64 half
+// tile), the stand-alone kernels fill entry 0; whoever writes entry 0 clears the entries nobody else writes.  finalize_kernel
+// sums all of them in index order.
+constexpr int GP_PER_TILE = 4;
 
 template <int LMAX, int E>
 __global__ void __launch_bounds__(256, LMAX == 4 ? POLY_GRAD_CTAS : POLY_GRAD8_CTAS) poly_grad_kernel(Batch b, int kind) {
@@ -574,7 +581,8 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? POLY_GRAD_CTAS : POLY_GRAD8_C
     int ti, tj;
     tri_decode(tile, ti, tj);
     double* out = b.grad_part + ((size_t)slot * ntiles + tile) * GP_PER_TILE * b.pstride;
-    if (threadIdx.x < b.pstride) out[b.pstride + threadIdx.x] = 0.0;
+    if (threadIdx.x < b.pstride)
+      for (int q = 1; q < GP_PER_TILE; q++) out[q * b.pstride + threadIdx.x] = 0.0;
     poly_grad_tile<LMAX, E, NB>(S, sb, b, slot, ti, tj, 0, b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB, b.Np, out);
   }
 }
@@ -618,12 +626,53 @@ __global__ void __launch_bounds__(TG_THREADS, 2) kinv_grad_kernel(Batch b) {
   tri_decode(bx, ti, tj);
   const int ntiles = tri_count(b.T);
   double* out = b.grad_part + (((size_t)slot * ntiles + bx) * GP_PER_TILE + hf) * b.pstride;
+  if (hf == 0 && threadIdx.x < b.pstride) { out[2 * b.pstride + threadIdx.x] = 0.0; out[3 * b.pstride + threadIdx.x] = 0.0; }
   poly_grad_tile<4, POLY_GE4, TG_TN>(S, sb, b, slot, ti, tj, hf * TG_TN, Kt, KG_LD, out);
 }
 
+// The same fusion on the 64 x 64 tiles of kinv64_kernel: three 4-warp CTAs per SM, so while one CTA contracts its K^-1 block
+// with dK/dtheta (element-wise FP64 work, latency-bound on its own) two others keep the DMMA pipe fed.
+constexpr int KG64_LD = K64_T + 2;
+static_assert(K64_T * KG64_LD * 8 + sizeof(PolySmem<4>) <= K64_SMEM_BYTES, "staged block + gradient tables fit the pipeline buffers");
+
+__global__ void __launch_bounds__(K64_THREADS, 3) kinv64_grad_kernel(Batch b) {
+  const int slot = b.slot0 + blockIdx.y;
+  if (b.slot_status[slot] != 0) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int I, J;
+  tri_decode(blockIdx.x, I, J);
+  const size_t ld = b.Np;
+  const double* V = b.M2 + slot * b.mstride;
+  double acc[TG_MT][TG_NT][2];
+  tile64_init(acc, nullptr, ld, 0.0);
+  tile64_pipeline(acc, V + (size_t)(I * K64_T) * ld + I * K64_T, V + (size_t)(J * K64_T) * ld + I * K64_T, ld,
+                  (b.Np - I * K64_T) / TG_KC, reinterpret_cast<double*>(smem_raw));
+  if (b.cprog[slot].kind != CK_POLY4) {      // uniform per CTA: K^-1 goes to HBM for the 5-8 leaf / interpreter kernels
+    tile64_store(acc, tile64_cw(b.M1 + slot * b.mstride + (size_t)(I * K64_T) * ld + J * K64_T, ld), ld, 1.0);
+    return;
+  }
+  __syncthreads();                           // every warp has left the pipeline stages
+  double* Kt = reinterpret_cast<double*>(smem_raw);
+  tile64_store(acc, tile64_cw(Kt, KG64_LD), KG64_LD, 1.0);
+  // (poly_grad_tile starts with a barrier: the staged block is complete before anybody reads it)
+  PolySmem<4>& S = *reinterpret_cast<PolySmem<4>*>(smem_raw + K64_T * KG64_LD * 8);
+  const unsigned sb = (unsigned)__cvta_generic_to_shared(&S);
+  const int ti = I >> 1, vi = I & 1, tj = J >> 1, vj = J & 1;
+  const int ntiles = tri_count(b.T);
+  double* out = b.grad_part + ((size_t)slot * ntiles + tri_count(ti) + tj) * GP_PER_TILE * b.pstride;
+  if (ti == tj && vi == 0 && threadIdx.x < b.pstride) out[1 * b.pstride + threadIdx.x] = 0.0;    // quadrant (0, 1) of a diagonal tile has no CTA
+  poly_grad_tile<4, POLY_GE4, K64_T, K64_THREADS, K64_T>(S, sb, b, slot, ti, tj, vj * K64_T, Kt - (size_t)(vi * K64_T) * KG64_LD,
+                                                         KG64_LD, out + (vi * 2 + vj) * b.pstride, vi * K64_T);
+}
+
 void launch_kinv_grad(const Batch& b, cudaStream_t s) {
-  dim3 grid(2 * tri_count(b.T), b.nslots);
-  kinv_grad_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b);
+  if (b.gemm64) {
+    dim3 grid(tri_count(2 * b.T), b.nslots);
+    kinv64_grad_kernel<<<grid, K64_THREADS, K64_SMEM_BYTES, s>>>(b);
+  } else {
+    dim3 grid(2 * tri_count(b.T), b.nslots);
+    kinv_grad_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b);
+  }
   g_launch_count++;
 }
 
@@ -746,7 +795,7 @@ __global__ void __launch_bounds__(256) interp_grad_kernel(Batch b) {
 #pragma unroll
       for (int q = 0; q < 8; q++) s += wred[q * b.pstride + p];
       out[p] = s;
-      out[b.pstride + p] = 0.0;
+      for (int q = 1; q < GP_PER_TILE; q++) out[q * b.pstride + p] = 0.0;
     }
   }
 }
@@ -884,6 +933,8 @@ int configure_kernels() {
     *c.grid = g_sm_count * (per_sm > 0 ? per_sm : 1);
   }
   e = cudaFuncSetAttribute(kinv_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(kinv64_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K64_SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
   return configure_chol_kernels();
 }

@@ -21,7 +21,7 @@ struct Batch {
   double* alpha;             // [slot][Np]  K^-1 y
   double* logdet_part;       // [slot][T]
   double* diag_part;         // [slot][T]   partial sums of diag(K_y) (jitter ladder)
-  double* grad_part;         // [slot][ntiles][2][pstride]: gradient partials per 128 x 64 half tile (elem_kernels.cu GP_PER_TILE)
+  double* grad_part;         // [slot][ntiles][4][pstride]: gradient partials per 64 x 64 quadrant of a tile (elem_kernels.cu GP_PER_TILE)
   double* solve_part;        // [slot][ntiles][NB] tile partials of z = V^T y, then of alpha = V z
   int pstride;
   int* slot_status;          // [slot] 0 ok, >0 = 1-based index of first bad pivot

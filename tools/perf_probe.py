@@ -16,6 +16,8 @@ def main():
     import os
     if os.environ.get('PANEL'): eng.set_panel_tiles(int(os.environ['PANEL']))
     if os.environ.get('QUIRKS'): eng.set_quirks(int(os.environ['QUIRKS']))
+    if os.environ.get('FUSED'): eng.set_fused_grad(int(os.environ['FUSED']))
+    if os.environ.get('TILE64'): eng.set_tile64(int(os.environ['TILE64']))
     batch = ProgramBatch(kernels)
     slots = eng.slots_for(n, 1, m, batch.max_params)
     print('slots', slots, 'max_params', batch.max_params, 'tokens', batch.tokens.shape)
