@@ -474,6 +474,21 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
   double acc[LMAX][3], accn = 0.0;
 #pragma unroll
   for (int l = 0; l < LMAX; l++) { acc[l][0] = 0.0; acc[l][1] = 0.0; acc[l][2] = 0.0; }
+  // <= 4 leaves: adjm[l] packs, one byte each, the terms containing leaf l with l's bit cleared and bit 4 set as a
+  // presence marker (a term that is the leaf alone has no other bit), so the row loop walks exactly the terms it needs
+  unsigned adjm[LMAX == 4 ? 4 : 1];
+  if (LMAX == 4) {
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      unsigned packed = 0u;
+      int n = 0;
+      for (int t = 0; t < G; t++) {
+        const unsigned mask = (terms4 >> (8 * t)) & 0xffu;
+        if (mask & (1u << l)) { packed |= ((mask & ~(1u << l)) | 16u) << (8 * n); n++; }
+      }
+      adjm[l] = packed;
+    }
+  }
   const double* Kinv = Kt + c;
   const int gj = tj * NB + col0 + c;
   // diagonal tiles: rows above this warp's first column hold no lower-triangle element
@@ -519,13 +534,22 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
           double adj[E];
 #pragma unroll
           for (int e = 0; e < E; e++) adj[e] = 0.0;
-          for (int t = 0; t < G; t++) {
-            const unsigned mask = term_mask<LMAX>(terms4, sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), t);
-            if (!(mask & (1u << l))) continue;
-            double p[E];
-            mask_product<LMAX, E>(v, mask & ~(1u << l), p);
+          if (LMAX == 4) {        // per-leaf list of the terms that contain the leaf, with the leaf removed: built once per tile
+            for (unsigned m = adjm[l]; m != 0u; m >>= 8) {
+              double p[E];
+              mask_product<LMAX, E>(v, (m & 0xffu) & 15u, p);
 #pragma unroll
-            for (int e = 0; e < E; e++) adj[e] += p[e];
+              for (int e = 0; e < E; e++) adj[e] += p[e];
+            }
+          } else {
+            for (int t = 0; t < G; t++) {
+              const unsigned mask = term_mask<LMAX>(terms4, sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), t);
+              if (!(mask & (1u << l))) continue;
+              double p[E];
+              mask_product<LMAX, E>(v, mask & ~(1u << l), p);
+#pragma unroll
+              for (int e = 0; e < E; e++) adj[e] += p[e];
+            }
           }
 #pragma unroll
           for (int e = 0; e < E; e++) g[e] = wt[e] * adj[e];
