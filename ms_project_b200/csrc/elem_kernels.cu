@@ -495,6 +495,7 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
   int rbeg = rbase + h * RPH;
   if (ti == tj) { const int cmin = col0 + c - lane; if (cmin > rbeg) rbeg = cmin / E * E; }
   const int rend = rbase + h * RPH + RPH;
+  const bool interior = ti > tj && (ti + 1) * NB <= b.N;
   double kv[E];
 #pragma unroll
   for (int e = 0; e < E; e++) kv[e] = (rbeg < rend) ? Kinv[(size_t)(rbeg + e) * kld] : 0.0;
@@ -502,13 +503,18 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
   for (int r0 = rbeg; r0 < rend; r0 += E) {
     double wt[E], ar[E];
     lds_rows<E>(sb + (unsigned)offsetof(SM, ai) + r0 * 8, ar);
+    if (interior) {          // tile strictly below the diagonal and inside N: every element is a valid symmetric pair
 #pragma unroll
-    for (int e = 0; e < E; e++) {
-      const int gi = ti * NB + r0 + e;
-      double wv = 0.5 * (ar[e] * aj - kv[e]);
-      const bool valid = gi < b.N && gj <= gi;       // gj <= gi < N
-      if (gi == gj) { if (valid) accn += wv; } else wv *= 2.0;      // symmetric pair (i, j), (j, i)
-      wt[e] = valid ? wv : 0.0;
+      for (int e = 0; e < E; e++) wt[e] = ar[e] * aj - kv[e];          // 2 * 0.5 * (alpha_i alpha_j - K^-1_ij)
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const int gi = ti * NB + r0 + e;
+        double wv = 0.5 * (ar[e] * aj - kv[e]);
+        const bool valid = gi < b.N && gj <= gi;       // gj <= gi < N
+        if (gi == gj) { if (valid) accn += wv; } else wv *= 2.0;      // symmetric pair (i, j), (j, i)
+        wt[e] = valid ? wv : 0.0;
+      }
     }
     if (r0 + E < rend) {
 #pragma unroll
