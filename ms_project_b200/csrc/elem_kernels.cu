@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? POLY_BUILD_CTAS : 2) poly_bui
                                              : (b.add_diag == 2 ? S.noise : 0.0);
     double* out = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB + c;
     const int gj = tj * NB + c;
+    const bool interior = ti > tj && (ti + 1) * NB <= b.N;
 #pragma unroll 1
     for (int r0 = h * 64; r0 < h * 64 + 64; r0 += E) {
       double v[LMAX][E], aux[E];
@@ -425,13 +426,18 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? POLY_BUILD_CTAS : 2) poly_bui
 #pragma unroll
         for (int e = 0; e < E; e++) k[e] += p[e];
       }
+      if (interior) {        // tile strictly below the diagonal and inside N: no padding, no diagonal element
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        const int gi = ti * NB + r0 + e;
-        double val = k[e];
-        if (gi >= b.N || gj >= b.N) val = (gi == gj) ? 1.0 : 0.0;
-        else if (gi == gj) { val += diag_add; S.ai[c] = val; }
-        out[(size_t)(r0 + e) * b.Np] = val;
+        for (int e = 0; e < E; e++) out[(size_t)(r0 + e) * b.Np] = k[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          const int gi = ti * NB + r0 + e;
+          double val = k[e];
+          if (gi >= b.N || gj >= b.N) val = (gi == gj) ? 1.0 : 0.0;
+          else if (gi == gj) { val += diag_add; S.ai[c] = val; }
+          out[(size_t)(r0 + e) * b.Np] = val;
+        }
       }
     }
     if (ti == tj) {    // deterministic partial of trace(K_y) for the jitter ladder
