@@ -11,9 +11,8 @@ fit (optimize_restarts), LML and predictions run through the same libb200gp pipe
 import numpy as np
 from scipy.special import erfc
 
-from .gpy_compat.gp import GP
+from .gpy_compat.gp import GPRegression
 from .gpy_compat.kern import RBFDistanceBuilderKernelKernel
-from .gpy_compat.likelihoods import Gaussian
 
 
 def set_priors(param, priors, in_place=False):
@@ -24,19 +23,6 @@ def set_priors(param, priors, in_place=False):
         if name in target.parameter_names():
             getattr(target, name).set_prior(getattr(prior, 'raw_prior', prior), warning=False)
     return target
-
-
-class GPRegression(GP):
-    """GPy.models.GPRegression: GP with a Gaussian likelihood of variance `noise_var` (gp_regression_models.py:80)."""
-
-    def __init__(self, X, Y, kernel, Y_metadata=None, normalizer=None, noise_var=1., mean_function=None):
-        super(GPRegression, self).__init__(X, Y, kernel, likelihood=Gaussian(variance=noise_var), name='GP regression',
-                                           normalizer=bool(normalizer), mean_function=mean_function)
-        self._role = 'surrogate'
-
-    @property
-    def Gaussian_noise(self):
-        return self.likelihood
 
 
 class KernelKernelGPModel(object):
@@ -149,8 +135,12 @@ class BayesOptGPStrategy(object):
         self.expansion_fn = expansion_fn
 
     def query(self, selected_models, fitness_scores, x_train, y_train):
-        """Index (into the active set) of the next model to evaluate; acquisition scores are left in `.score` of every
-        unevaluated model, as the reference does."""
+        """The next model to evaluate (bayes_opt_gp_strategy.py:35-115).  Acquisition scores are left in `.score` of every
+        candidate of the active set, as the reference does; the RETURNED model is a fresh, un-evaluated `GPModel` around
+        the chosen covariance ("Reinitialize to get rid of acquisition score", :97-101), so the evaluation loop fits it
+        instead of mistaking its acquisition value for a fitness.  Its active-set index is `self.last_selected_index`
+        (also appended to `active_models.selected_indices`)."""
+        from .gp_model import GPModel
         generation = len(selected_models)
         meta_x = np.array(self.active_models.selected_indices)[:, None]
         meta_y = np.array(fitness_scores, dtype=np.float64)[:, None]
@@ -173,5 +163,8 @@ class BayesOptGPStrategy(object):
             candidates = sorted(set(range(len(self.active_models))) - set(selected))
         scores = [self.active_models.models[i].score for i in candidates]
         nxt = candidates[int(np.nanargmax([scores]))]
+        chosen = self.active_models.models[nxt]
+        next_model = GPModel(chosen.covariance, getattr(chosen, 'likelihood', None))
         self.active_models.selected_indices += [nxt]
-        return nxt
+        self.last_selected_index = nxt
+        return next_model

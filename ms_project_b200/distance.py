@@ -87,6 +87,48 @@ def get_priors(kernel):
     return priors
 
 
+def cov_nearest(cov, method='clipped', threshold=1e-15, n_fact=100, return_all=False):
+    """`statsmodels.stats.correlation_tools.cov_nearest` as the reference calls it (`cov_nearest(k, threshold=tolerance)`,
+    distance.py:296: the default 'clipped' method; statsmodels is not installable here, so its published algorithm is
+    restated): covariance -> correlation, eigenvalues below `threshold` clipped to it (corr_clipped / clip_evals, one
+    symmetric eigendecomposition), re-normalised to unit diagonal, scaled back by the original standard deviations.
+    The rare repair path of `chol_safe`: host NumPy, like the reference."""
+    if method != 'clipped':
+        raise NotImplementedError("only method='clipped' (the default the reference uses) is restated")
+    cov = np.asanyarray(cov, dtype=np.float64)
+    std_ = np.sqrt(np.diag(cov))
+    corr = cov / np.outer(std_, std_)
+    evals, evecs = np.linalg.eigh(corr)                # raises LinAlgError for a non-square input (test_distance.py:119-121)
+    if np.any(evals < threshold):
+        corr = np.dot(evecs * np.maximum(evals, threshold), evecs.T)
+        x_std = np.sqrt(np.diag(corr))
+        corr = corr / x_std / x_std[:, None]
+    cov_ = corr * np.outer(std_, std_)
+    return (cov_, corr, std_) if return_all else cov_
+
+
+def fix_numerical_problem(k, tolerance):
+    """distance.py:287-298."""
+    k = cov_nearest(k, threshold=tolerance)
+    return np.linalg.cholesky(k).T
+
+
+def chol_safe(k, tolerance):
+    """distance.py:300-312: plain Cholesky (upper factor), repaired through cov_nearest when it fails."""
+    try:
+        return np.linalg.cholesky(k).T
+    except np.linalg.LinAlgError:
+        return fix_numerical_problem(k, tolerance)
+
+
+def _repaired_logdet(k, tolerance):
+    """log-determinant the reference ends up with when its np.linalg.cholesky has failed (the device reported status 1):
+    2 sum log diag(chol(cov_nearest(k)))."""
+    with np.errstate(all='ignore'):
+        c = fix_numerical_problem(np.asarray(k, dtype=np.float64), tolerance)
+        return float(2.0 * np.sum(np.log(np.diag(c)), axis=0))
+
+
 class ActiveModels(object):
     """Minimal stand-in for ActiveSet (src/autoks/core/active_set.py): an indexable model store."""
 
@@ -225,7 +267,28 @@ class HellingerDistanceBuilder(DistanceBuilder):
         self._d_logdet.index_copy_(0, sel, d_ld)
         self._d_G.index_copy_(0, sel, d_G)
         ld_host, st_host = d_ld.cpu().numpy(), d_st.cpu().numpy()
+        self._finish_precompute(active_models, idx, kernels, hyps, ld_host, st_host)
+
+    precompute_tolerance = 1e-6       # `tolerance` of create_precomputed_info (distance.py:174)
+
+    def _finish_precompute(self, active_models, idx, kernels, hyps, ld_host, st_host):
+        """Host epilogue of a precompute: (1) a Gram matrix whose plain Cholesky failed on the device (status 1) gets the
+        log-determinant `chol_safe` arrives at through `cov_nearest` (distance.py:190-191, 287-312); (2) the reference's
+        loop leaves every kernel at its LAST prior sample (`covariance.raw_kernel[:] = hyp`, distance.py:186, never
+        restored), which is where a later fit's restart 0 starts from -- reproduced."""
+        torch = self.engine.torch
+        if self._needs_logdet and np.any(st_host != 0):
+            for j, s in zip(*np.nonzero(st_host)):
+                G = self._d_G[idx[j], s].cpu().numpy()
+                try:
+                    ld_host[j, s] = _repaired_logdet(G, self.precompute_tolerance)
+                    st_host[j, s] = 0
+                except np.linalg.LinAlgError:
+                    ld_host[j, s] = np.nan
+            sel = torch.tensor(idx, dtype=torch.long, device=self.engine.device)
+            self._d_logdet.index_copy_(0, sel, torch.from_numpy(np.ascontiguousarray(ld_host)).to(self.engine.device))
         for j, i in enumerate(idx):
+            kernels[j][:] = hyps[j][-1]
             active_models.models[i].info = HellingerInfo(self, i, ld_host[j].copy(), st_host[j].copy())
 
     _needs_logdet = True        # the vector builders (Frobenius / correlation) only need the Gram matrices
@@ -250,9 +313,8 @@ class HellingerDistanceBuilder(DistanceBuilder):
         sel = torch.tensor(idx, dtype=torch.long, device=eng.device)
         self._d_logdet.index_copy_(0, sel, d_ld.view(M, S))
         self._d_G.index_copy_(0, sel, d_G.view(M, S, n, n))
-        ld_host, st_host = d_ld.view(M, S).cpu().numpy(), d_st.view(M, S).cpu().numpy()
-        for j, i in enumerate(idx):
-            active_models.models[i].info = HellingerInfo(self, i, ld_host[j].copy(), st_host[j].copy())
+        ld_host, st_host = d_ld.view(M, S).cpu().numpy().copy(), d_st.view(M, S).cpu().numpy().copy()
+        self._finish_precompute(active_models, idx, kernels, hyps, ld_host, st_host)
 
     def _pair_distances_large(self, pi, pj):
         """n > 128: the host lists the (pair, sample) cells hellinger_distance refactorises (|ld_i - ld_j| > tol,
@@ -326,10 +388,30 @@ class HellingerDistanceBuilder(DistanceBuilder):
                 ii.append(int(i))
                 jj.append(int(j))
         dist, status = self.pair_distances(ii, jj)
+        dist, status = self._repair_pairs(ii, jj, dist, status)
         self.last_status = status
         for i, j, d in zip(ii, jj, dist):
             self._average_distance[i, j] = d
             self._average_distance[j, i] = d
+
+    def _repair_pairs(self, ii, jj, dist, status):
+        """Pairs for which some 1/2 (G_i + G_j) failed its plain Cholesky on the device (status 1, distance NaN): the
+        reference's chol_safe repairs such a matrix through cov_nearest (distance.py:153, 300-312) -- redone here on the
+        host for exactly those pairs (rare; eigendecompositions stay on the CPU)."""
+        bad = np.nonzero(np.asarray(status) != 0)[0]
+        if bad.size == 0:
+            return dist, status
+        dist, status = np.array(dist, dtype=np.float64), np.array(status)
+        ld = self._d_logdet.cpu().numpy()
+        for k in bad:
+            i, j = int(ii[k]), int(jj[k])
+            try:
+                dist[k] = _hellinger_distance_host(ld[i], self.mini_gram_matrices(i), ld[j], self.mini_gram_matrices(j),
+                                                   self.tol_logdet)
+                status[k] = 0
+            except np.linalg.LinAlgError:
+                dist[k] = np.nan
+        return dist, status
 
     @staticmethod
     def metric(data_i, data_j, **kwargs):
@@ -364,6 +446,8 @@ class HellingerDistanceBuilder(DistanceBuilder):
                                                              d_pj.data_ptr(), 1, d_wp.data_ptr(), d_ws.data_ptr(), int(ws.size),
                                                              work.data_ptr(), d_dist.data_ptr(), d_st.data_ptr())
                 _lib.check(engine.ctx, rc, 'b200gp_hellinger_pairs_large')
+                if int(d_st.cpu().numpy()[0]) != 0:
+                    return _hellinger_distance_host(log_det_i, mini_gram_matrices_i, log_det_j, mini_gram_matrices_j, tol)
                 return float(d_dist.cpu().numpy()[0])
         work = torch.empty(engine.lib.b200gp_hellinger_pairs_work_bytes(1, S), dtype=torch.uint8, device=engine.device)
         d_dist = torch.empty(1, dtype=torch.float64, device=engine.device)
@@ -372,7 +456,23 @@ class HellingerDistanceBuilder(DistanceBuilder):
                                                d_pj.data_ptr(), 1, ctypes.c_double(tol), work.data_ptr(), d_dist.data_ptr(),
                                                d_st.data_ptr())
         _lib.check(engine.ctx, rc, 'b200gp_hellinger_pairs')
+        if int(d_st.cpu().numpy()[0]) != 0:
+            return _hellinger_distance_host(log_det_i, mini_gram_matrices_i, log_det_j, mini_gram_matrices_j, tol)
         return float(d_dist.cpu().numpy()[0])
+
+
+def _hellinger_distance_host(log_det_i, G_i, log_det_j, G_j, tol):
+    """hellinger_distance (distance.py:135-168) for ONE pair whose device evaluation reported a failed factorisation:
+    every factorisation goes through chol_safe, so the failing ones get the cov_nearest repair."""
+    log_det_i, log_det_j = np.asarray(log_det_i, dtype=np.float64), np.asarray(log_det_j, dtype=np.float64)
+    with np.errstate(invalid='ignore'):
+        different = np.abs(log_det_i - log_det_j) > tol
+    ldpq = log_det_i.copy()
+    for s in np.nonzero(different)[0]:
+        c = chol_safe(0.5 * (G_i[:, :, s] + G_j[:, :, s]), tol)
+        ldpq[s] = 2 * np.sum(np.log(np.diag(c)), axis=0)
+    hellinger = 1 - np.exp(0.25 * (log_det_i + log_det_j) - 0.5 * ldpq)
+    return float(np.sqrt(np.clip(np.mean(hellinger, axis=0), 0, 1)))
 
 
 class _VectorInfo(object):

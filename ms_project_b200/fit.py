@@ -31,14 +31,17 @@ def check_optimizer(optimizer):
 
 
 class _PriorTable(object):
-    """Flat per-parameter prior description in device theta layout."""
+    """Flat per-parameter prior description in device theta layout.  Gaussian / LogGaussian (the only families the
+    reference's hyperprior tables use, core/hyperprior.py:54-112) are vectorised; any other prior object is applied
+    through its own lnpdf / lnpdf_grad, grouped per instance."""
 
     def __init__(self, priors):
         n = len(priors)
-        self.kind = np.zeros(n, dtype=np.int8)     # 0 none, 1 LogGaussian, 2 Gaussian
+        self.kind = np.zeros(n, dtype=np.int8)     # 0 none, 1 LogGaussian, 2 Gaussian, 3 other
         self.mu = np.zeros(n)
         self.s2 = np.ones(n)
         self.const = np.zeros(n)
+        other = {}
         for i, p in enumerate(priors):
             if p is None:
                 continue
@@ -46,9 +49,14 @@ class _PriorTable(object):
                 self.kind[i] = 1
             elif type(p) is _GaussianPrior:
                 self.kind[i] = 2
+            elif hasattr(p, 'lnpdf') and hasattr(p, 'lnpdf_grad'):
+                self.kind[i] = 3
+                other.setdefault(id(p), (p, []))[1].append(i)
+                continue
             else:
                 raise NotImplementedError('prior %s is not supported on the scoring path' % type(p).__name__)
             self.mu[i], self.s2[i], self.const[i] = p.mu, p.sigma2, p.constant
+        self.other = [(p, np.asarray(ix, dtype=int)) for p, ix in other.values()]
         self.has = self.kind != 0
         self.lg = self.kind == 1
         self.ga = self.kind == 2
@@ -68,6 +76,9 @@ class _PriorTable(object):
                 t = theta[self.ga]
                 lp[self.ga] = self.const[self.ga] - 0.5 * np.square(t - self.mu[self.ga]) / self.s2[self.ga]
                 dlp[self.ga] = -(t - self.mu[self.ga]) / self.s2[self.ga]
+            for p, ix in self.other:
+                lp[ix] = p.lnpdf(theta[ix])
+                dlp[ix] = p.lnpdf_grad(theta[ix])
             if self.has.any():
                 t = theta[self.has]
                 lp[self.has] += _LOGEXP.log_jacobian(t)

@@ -113,65 +113,109 @@ def plan_evaluation(models, n_evals, eval_budget, visited, skip_evaluated=True):
     return to_fit, order
 
 
-def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engine=None, model_dict=None,
-                 all_models=None, shard=None, overlap=None):
+def _waves(models):
+    """Models that share ONE kernel object (the random grammars hand out `grammar.base_kernels[i]` itself, so a candidate
+    list may hold `RQ_1` several times as the same object) are a sequential chain in the reference: the second occurrence
+    starts its restart 0 from the optimum the first one wrote into the shared object (gp_model.py:61-79).  Wave w holds the
+    w-th occurrence of every kernel object; waves run one after the other, everything inside a wave in one batch."""
+    seen, waves = {}, []
+    for i, m in enumerate(models):
+        w = seen.get(id(m.covariance.raw_kernel), 0)
+        seen[id(m.covariance.raw_kernel)] = w + 1
+        while len(waves) <= w:
+            waves.append([])
+        waves[w].append(i)
+    return waves
+
+
+def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engine=None, model_dict=None, overlap=None,
+                 comm=None):
     """GPModel.score_model for a whole list in ONE lock-step GPU batch (same per-model results and side effects as
-    calling score_model on each, including the retry-once rule and failed_fitting)."""
+    calling score_model on each, including the retry-once rule and failed_fitting).
+
+    Restart points come from the global np.random in the reference's order (model-major, restart-minor), all drawn before
+    the batch runs.  Retry-once (gp_model.py:67-77): the models whose LML came back +-inf are re-fitted in a second batch
+    whose restart points are drawn AFTER the first batch, in list order -- the reference draws them right after the failing
+    model, so the streams differ from the first retry on (hazard 5).
+
+    `comm` (parallel.Comm, None = this process alone) shards every batch over the ranks of a torch.distributed group:
+    each rank fits its slice, one all_gather of fixed-width records writes scores and optimised parameters into EVERY
+    rank's model objects.  Every rank draws the restart points of the WHOLE list and -- after the failure flags have been
+    all-gathered -- the retry points of EVERY failing model, so np.random stays in the same state on all ranks and the search
+    loop continues identically everywhere."""
     check_optimizer(optimizer)
-    if all_models is not None:
-        # sharded run: draw the restart points of the WHOLE list (identical on every rank), keep our slice
-        all_gps = []
-        for m in all_models:
-            _prepare(m, model_dict)
-            all_gps.append(m.build_model(x, y))
-        from .fit import draw_starts
-        starts_all = draw_starts([g.kern for g in all_gps], [g.likelihood for g in all_gps], n_restarts)
-        starts = starts_all[shard[0]:shard[1]]
-    else:
-        starts = None
+    from .fit import draw_starts
     if not models:
         return []
-    if engine is None:
-        from .engine import get_engine
-        engine = get_engine(0)
+    R = max(int(n_restarts), 1)
     gps = []
     for m in models:
         _prepare(m, model_dict)
         gps.append(m.build_model(x, y))
-    maxp = max(g.kern.size for g in gps)
-    n_inst = len(gps) * max(int(n_restarts), 1)
-    if overlap is None:
-        overlap = len(gps) >= 16         # enough instances for two lock-step drivers to keep the GPU busy
-    if overlap:
-        # two host threads, two engines on the same GPU (fit.fit_models_overlapped): host L-BFGS-B work of one group
-        # hides behind the device batch of the other
-        engines = [engine, engine.peer()]
-        for e in engines:
-            e.ensure_bound(x, y, (n_inst + 1) // 2, maxp)
-        results = fit_models_overlapped(engines, [g.kern for g in gps], [g.likelihood for g in gps], num_restarts=n_restarts,
-                                        robust=True, starts=starts, optimizer=optimizer)
-    else:
+    starts = draw_starts([g.kern for g in gps], [g.likelihood for g in gps], n_restarts)
+    if engine is None:
+        from .engine import get_engine
+        engine = get_engine(0)
+    n_data = np.asarray(x).shape[0]
+
+    def fit(idx, st):
+        if not idx:
+            return []
+        ks, ls = [gps[i].kern for i in idx], [gps[i].likelihood for i in idx]
+        maxp = max(k.size for k in ks)
+        n_inst = len(idx) * R
+        two = (len(idx) >= 16) if overlap is None else (overlap and len(idx) >= 4)
+        if two:
+            # two host threads, two engines on the same GPU (fit.fit_models_overlapped): host L-BFGS-B work of one group
+            # hides behind the device batch of the other
+            engines = [engine, engine.peer()]
+            for e in engines:
+                e.ensure_bound(x, y, (n_inst + 1) // 2, maxp)
+            return fit_models_overlapped(engines, ks, ls, num_restarts=n_restarts, robust=True, starts=st, optimizer=optimizer)
         engine.ensure_bound(x, y, n_inst, maxp)
-        results = fit_models(engine, [g.kern for g in gps], [g.likelihood for g in gps], num_restarts=n_restarts, robust=True,
-                             starts=starts, optimizer=optimizer)
-    for g, r in zip(gps, results):
-        g._lml, g._status = r.lml, r.status
-        g.optimization_runs += r.runs
-    retry = [i for i, g in enumerate(gps) if _is_bad(g.log_likelihood())]
-    if retry:
-        engine.ensure_bound(x, y, len(retry) * max(int(n_restarts), 1), maxp)
-        rr = fit_models(engine, [gps[i].kern for i in retry], [gps[i].likelihood for i in retry], num_restarts=n_restarts,
-                        robust=True, optimizer=optimizer)
-        for i, r in zip(retry, rr):
+        return fit_models(engine, ks, ls, num_restarts=n_restarts, robust=True, starts=st, optimizer=optimizer)
+
+    for w, wave in enumerate(_waves(models)):
+        if w > 0:                       # restart 0 = the parameters the previous occurrence of the shared object left behind
+            for i in wave:
+                starts[i][0] = np.concatenate([gps[i].kern.param_array, gps[i].likelihood.param_array])
+        mine = wave if comm is None else comm.shard(wave, [model_cost(gps[i].kern, n_data) for i in wave])
+        results = dict(zip(mine, fit(mine, [starts[i] for i in mine])))
+        for i, r in results.items():
             gps[i]._lml, gps[i]._status = r.lml, r.status
+            gps[i].optimization_runs += r.runs
+        bad = [i for i in mine if _is_bad(gps[i].log_likelihood())]
+        if comm is not None:
+            bad = comm.union(bad)       # who failed, over the whole wave, identical on every rank
+        # retry points of every failing model of the wave, in list order, drawn on every rank (restart 0 = the model's
+        # current, i.e. optimised, parameters: only the owner holds them and only the owner uses them)
+        retry_starts = {i: draw_starts([gps[i].kern], [gps[i].likelihood], n_restarts)[0] for i in sorted(bad)}
+        retry = [i for i in sorted(bad) if i in results]
+        for i, r in zip(retry, fit(retry, [retry_starts[i] for i in retry])):
+            gps[i]._lml, gps[i]._status = r.lml, r.status
+            gps[i].optimization_runs += r.runs
+            r.n_evals += results[i].n_evals
+            results[i] = r                                     # the record (lml, theta) of the fit that stands
             if _is_bad(gps[i].log_likelihood()):
                 models[i].failed_fitting = True
-    for m, g, r in zip(models, gps, results):
-        m.covariance.raw_kernel = g.kern
-        m.likelihood = g.likelihood
-        m.fit_result = r
-        m.score = scoring_func(g) if not m.failed_fitting else np.nan
+        for i in mine:
+            m, g = models[i], gps[i]
+            m.covariance.raw_kernel = g.kern
+            m.likelihood = g.likelihood
+            m.fit_result = results[i]
+            m.score = scoring_func(g) if not m.failed_fitting else np.nan
+        if comm is not None:
+            comm.exchange(models, wave, mine)
     return [m.score for m in models]
+
+
+def model_cost(kernel, n_data):
+    """Relative cost of fitting one model, for balancing shards: per evaluation N^3 for the factorisation + inverse plus the
+    element-wise passes that scale with the number of leaves, times the number of evaluations an L-BFGS-B
+    run needs, which grows with the number of parameters."""
+    n_params = kernel.size + 1
+    n_leaves = sum(1 for _ in kernel.flattened_parameters()) / 2.5 + 1.0
+    return (float(n_data) ** 3 + 150.0 * n_leaves * float(n_data) ** 2) * (10.0 + 4.0 * n_params)
 
 
 def _prepare(m, model_dict):

@@ -8,4 +8,5 @@ from .kern import Kern, RBF, RationalQuadratic, StandardPeriodic, LinScaleShift,
 from .priors import Prior, Gaussian, LogGaussian  # noqa: F401
 from .likelihoods import Likelihood  # noqa: F401,E402
 from . import likelihoods  # noqa: F401,E402
-from .gp import GP  # noqa: F401,E402
+from .gp import GP, GPRegression  # noqa: F401,E402
+from .inference import Laplace, ExactGaussianInference  # noqa: F401,E402

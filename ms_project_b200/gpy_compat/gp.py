@@ -148,3 +148,20 @@ class GP(Parameterized):
         if status == 2:
             raise np.linalg.LinAlgError('not positive definite, even with jitter.')
         return (mean * self._y_std + self._y_mean)[:, None], (var * self._y_std ** 2)[:, None]
+
+
+class GPRegression(GP):
+    """`GPy.models.GPRegression(X, Y, kernel, normalizer=, noise_var=)`: a GP with a Gaussian likelihood, as
+    KernelKernelGPModel._create_model builds it (src/autoks/gp_regression_models.py:79-80)."""
+
+    def __init__(self, X, Y, kernel=None, Y_metadata=None, normalizer=None, noise_var=1., mean_function=None):
+        if kernel is None:
+            from .kern import RBF
+            kernel = RBF(np.asarray(X).shape[1])
+        super(GPRegression, self).__init__(X, Y, kernel, Gaussian(variance=noise_var), mean_function=mean_function,
+                                           name='GP regression', Y_metadata=Y_metadata, normalizer=bool(normalizer))
+        self._role = 'surrogate'       # its own engine: a surrogate fitted in the middle of a search leaves the search's bound data alone
+
+    @property
+    def Gaussian_noise(self):
+        return self.likelihood

@@ -62,6 +62,13 @@ class Param(object):
     def parameter_names(self):
         return [self.name]
 
+    @property
+    def priors(self):
+        return PriorIndex([self])
+
+    def flattened_parameters(self):
+        return [self]
+
     def traverse(self, fn, *a, **kw):
         fn(self, *a, **kw)
 
@@ -155,7 +162,20 @@ class Parameterized(object):
             p._v[0] = v
 
     def __getitem__(self, item):
+        if isinstance(item, str):
+            return self._by_name(item)
         return self.param_array[item]
+
+    def _by_name(self, pattern):
+        """paramz's `obj['regexp']`: the parameter(s) whose hierarchical name matches (test_backend_kernel.py:70 reads
+        `kernel['variance'].priors`).  One match -> that Param, several -> the list."""
+        import re
+        rx = re.compile(pattern)
+        names = self.parameter_names()
+        hits = [p for n, p in zip(names, self.flattened_parameters()) if rx.match(n) or rx.match(n.split('.')[-1])]
+        if not hits:
+            raise AttributeError('no parameter matches %r' % pattern)
+        return hits[0] if len(hits) == 1 else hits
 
     def parameter_names(self, add_self=False, adjust_for_printing=False, recursive=True):
         names = []

@@ -35,11 +35,17 @@ def shard_bounds(costs, world_size):
     return bounds
 
 
-def model_cost(kernel, n_data):
-    """Relative cost of one LML+grad evaluation: N^3 for the factorisation + inverse, plus the element-wise
-    passes that scale with the number of leaves."""
-    n_leaves = sum(1 for _ in kernel.flattened_parameters()) / 2.5 + 1.0
-    return float(n_data) ** 3 + 150.0 * n_leaves * float(n_data) ** 2
+def lpt_assign(costs, world_size):
+    """Longest-processing-time-first: items in descending cost order, each to the least-loaded rank (ties: lowest rank).
+    Returns `owner[item]`.  Deterministic, so every rank computes the same assignment without talking."""
+    costs = np.asarray(costs, dtype=np.float64)
+    load = np.zeros(world_size)
+    owner = np.zeros(costs.size, dtype=np.int64)
+    for i in np.argsort(-costs, kind='stable'):
+        r = int(np.argmin(load))
+        owner[i] = r
+        load[r] += costs[i]
+    return owner
 
 
 def all_gather_records(local, counts, device=None):
@@ -64,50 +70,77 @@ def all_gather_records(local, counts, device=None):
     return np.concatenate([out[r, :counts[r]] for r in range(ws)], axis=0)
 
 
+class Comm(object):
+    """What gp_model.score_models needs from the process group: who fits what, who failed, and the record exchange."""
+
+    def __init__(self, policy='lpt'):
+        self.rank, self.ws = world()
+        self.policy = policy
+        self._owner = None
+
+    def shard(self, items, costs):
+        """The members of `items` (indices into the model list) this rank fits.  'lpt': balanced by the a-priori cost;
+        'contiguous': balanced contiguous ranges."""
+        items = list(items)
+        if self.policy == 'contiguous':
+            bounds = shard_bounds(costs, self.ws)
+            owner = np.zeros(len(items), dtype=np.int64)
+            for r in range(self.ws):
+                owner[bounds[r]:bounds[r + 1]] = r
+        else:
+            owner = lpt_assign(costs, self.ws)
+        self._owner = owner
+        return [it for it, o in zip(items, owner) if o == self.rank]
+
+    def union(self, local_items):
+        """Union over ranks of small index lists (the models that need a retry), sorted."""
+        counts_local = np.array([[float(len(local_items))]])
+        counts = [int(c) for c in all_gather_records(counts_local, [1] * self.ws)[:, 0]]
+        rec = np.asarray(local_items, dtype=np.float64).reshape(-1, 1)
+        return sorted(int(v) for v in all_gather_records(rec, counts)[:, 0])
+
+    def exchange(self, models, items, mine):
+        """All-gather {index, score, lml, failed, n_evals, theta...} of the models each rank fitted and write them into
+        every rank's model objects."""
+        from . import fit as _fit
+        from .gpy_compat.likelihoods import Gaussian
+        pmax = max(models[i].covariance.raw_kernel.size for i in items) + 1
+        rec = np.zeros((len(mine), 6 + pmax))
+        for k, i in enumerate(mine):
+            m = models[i]
+            th = np.concatenate([m.covariance.raw_kernel.param_array, m.likelihood.param_array])
+            r = m.fit_result
+            rec[k, :6] = [i, m.score, r.lml, float(m.failed_fitting), r.n_evals, th.size]
+            rec[k, 6:6 + th.size] = th
+        counts = [int(np.sum(self._owner == r)) for r in range(self.ws)]
+        mine_set = set(mine)
+        for row in all_gather_records(rec, counts):
+            i, p = int(row[0]), int(row[5])
+            if i in mine_set:
+                continue
+            m = models[i]
+            m.covariance.raw_kernel[:] = row[6:6 + p - 1]
+            m.covariance.raw_kernel = m.covariance.raw_kernel            # re-tokenise like gp_model.py:79
+            if m.likelihood is None:
+                m.likelihood = Gaussian()
+            m.likelihood[:] = row[6 + p - 1:6 + p]
+            m.failed_fitting = bool(row[3])
+            m.score = float(row[1])
+            r = _fit.FitResult()
+            r.lml, r.n_evals, r.theta = float(row[2]), int(row[4]), np.array(row[6:6 + p])
+            m.fit_result = r
+
+
 def score_models_sharded(models, x, y, scoring_func, optimizer=None, n_restarts=10, engine=None, model_dict=None,
-                         score_fn=None):
-    """`score_models` across all ranks: every rank holds the full candidate list, fits only its shard, then the
-    records {score, lml, failed, n_evals, n_params, theta...} are all-gathered and written into EVERY rank's model
-    objects, so the search loop continues identically everywhere.  Restart draws are made for the whole list on
-    every rank (same global seed => same draws as a single-GPU run), each rank using its own slice."""
-    from . import fit as _fit
+                         policy='lpt'):
+    """`gp_model.score_models` across all ranks: every rank holds the full candidate list, fits only its share, then the
+    records are all-gathered and written into EVERY rank's model objects, so the search loop continues identically
+    everywhere.  Restart draws are made for the whole list on every rank (same global seed => same draws as a single-GPU
+    run); results are bit-identical to the single-GPU fit because every (model, restart) instance is an independent
+    optimisation and no device reduction depends on the batch composition."""
     from .gp_model import score_models
-    rank, ws = world()
-    n = len(models)
-    if n == 0:
-        return []
-    if score_fn is None:
-        score_fn = score_models
-    costs = [model_cost(m.covariance.raw_kernel, np.asarray(x).shape[0]) for m in models]
-    bounds = shard_bounds(costs, ws)
-    lo, hi = bounds[rank], bounds[rank + 1]
-    counts = [bounds[r + 1] - bounds[r] for r in range(ws)]
-    mine = models[lo:hi]
-    score_fn(mine, x, y, scoring_func, optimizer=optimizer, n_restarts=n_restarts, engine=engine, model_dict=model_dict,
-             all_models=models, shard=(lo, hi))
-    pmax = max(m.covariance.raw_kernel.size for m in models) + 1
-    rec = np.zeros((len(mine), 5 + pmax))
-    for i, m in enumerate(mine):
-        th = np.concatenate([m.covariance.raw_kernel.param_array, m.likelihood.param_array])
-        r = m.fit_result
-        rec[i, 0] = m.score
-        rec[i, 1] = np.nan if r is None else r.lml
-        rec[i, 2] = float(m.failed_fitting)
-        rec[i, 3] = 0 if r is None else r.n_evals
-        rec[i, 4] = th.size
-        rec[i, 5:5 + th.size] = th
-    full = all_gather_records(rec, counts)
-    for m, row in zip(models, full):
-        p = int(row[4])
-        m.covariance.raw_kernel[:] = row[5:5 + p - 1]
-        m.covariance.raw_kernel = m.covariance.raw_kernel            # re-tokenise like gp_model.py:79
-        if m.likelihood is None:
-            from .gpy_compat.likelihoods import Gaussian
-            m.likelihood = Gaussian()
-        m.likelihood[:] = row[5 + p - 1:5 + p]
-        m.failed_fitting = bool(row[2])
-        m.score = float(row[0])
-    return [m.score for m in models]
+    return score_models(models, x, y, scoring_func, optimizer=optimizer, n_restarts=n_restarts, engine=engine,
+                        model_dict=model_dict, comm=Comm(policy) if world()[1] > 1 else None)
 
 
 def hellinger_matrix_sharded(builder, active_models, n_models):

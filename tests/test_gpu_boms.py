@@ -130,9 +130,35 @@ def test_query_step_selects_an_unevaluated_model(engine):
     fitness = [0.2, 0.5]
     chosen = []
     for step in range(3):
-        nxt = strategy.query([am.models[i] for i in am.selected_indices], fitness, None, None)
+        model = strategy.query([am.models[i] for i in am.selected_indices], fitness, None, None)
+        nxt = strategy.last_selected_index
         assert nxt not in am.selected_indices[:-1] and am.selected_indices[-1] == nxt
         assert all(am.models[i].score is not None for i in am.get_candidate_indices())
+        # the returned model is fresh (bayes_opt_gp_strategy.py:97-101): the evaluation loop must FIT it, not keep its EI value
+        assert model.covariance is am.models[nxt].covariance and not model.evaluated and np.isnan(model.score)
         chosen.append(nxt)
         fitness.append(float(rng.rand()))
     assert len(set(chosen)) == 3
+
+
+def test_queried_model_is_fitted_by_the_evaluation_loop(engine):
+    """query -> evaluate_models: the chosen model goes through plan_evaluation as 'fit' and ends with a fitness (nBIC of a
+    fitted GP), not with the acquisition value that query left on the active set's entry."""
+    from ms_project_b200 import fitness as F
+    from ms_project_b200.boms import BayesOptGPStrategy, expected_improvement
+    from ms_project_b200.gp_model import BatchedEvaluator, plan_evaluation
+    am, builder, hp = _pool(12)
+    strategy = BayesOptGPStrategy(am, expected_improvement, builder, {'SE': hp['SE'], 'GP': hp['GP']}, optimize_restarts=2)
+    np.random.seed(2)
+    am.selected_indices = [0, 3]
+    model = strategy.query([am.models[i] for i in am.selected_indices], [0.2, 0.5], None, None)
+    ei = am.models[strategy.last_selected_index].score
+    to_fit, order = plan_evaluation([model], 0, 10, set())
+    assert to_fit == [model] and order[0][1] == 'fit'
+    rng = np.random.RandomState(0)
+    X = rng.rand(40, 2)
+    y = rng.randn(40, 1)
+    ev = BatchedEvaluator(F.negative_bic, n_restarts_optimizer=2, engine=engine)
+    out = ev.evaluate_models([model], X, y, eval_budget=10)
+    assert out == [model] and model.evaluated and np.isfinite(model.score) and model.score != ei
+    assert model.fit_result is not None and model.fit_result.n_evals > 0
