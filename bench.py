@@ -9,9 +9,13 @@ evaluation of every item (the unit an L-BFGS-B iteration of `optimize_restarts` 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 N > 1 is launched by torchrun (one rank per GPU); candidates shard across ranks with no traffic during
-scoring and one NCCL all_gather of the scores per step (weak scaling: 768 items per GPU).
+scoring and one NCCL all_gather of the scores per step (weak scaling: 768 items per GPU).  The same line carries the
+STRONG-scaling legs (fixed total work sharded over the N ranks through parallel.score_models_sharded): `fit` = the whole
+C2 configuration fitted (256 candidates x 3 restarts), `strong_c4` = one C4 generation (512 candidates, N = 4096, D = 8):
+one NLML+grad evaluation of the population and a 3-restart fit with a stated optimiser budget.
 `--impl reference` times the CPU oracle (the NumPy/SciPy-LAPACK restatement of the reference's GPy path --
-GPy itself is not installable) on the host cores, on a bounded sample of the same items.
+GPy itself is not installable) on ALL host cores -- a process pool, one candidate per core, BLAS threads = 1,
+the analogue of src/training/run_experiment_from_file.py:81-84 -- on a stratified sample of the same 768 items.
 """
 import argparse
 import json
@@ -31,6 +35,23 @@ UNIT = 'kernels/s'
 N_DATA = 2048
 N_KERNELS = 256
 N_RESTARTS = 3
+C4_MAX_ITERS = 10          # optimiser budget of the C4 strong-scaling fit (stated in the line; paramz's default is 1000)
+
+
+def shared_config(world):
+    """`config` of BOTH arms (ours and --impl reference): same keys, same values."""
+    n_items = N_KERNELS * N_RESTARTS
+    return {'workload': 'C2: 256 random CKS-grammar kernels x 3 restart draws = 768 (kernel, theta) items per GPU, '
+                        'N=2048, D=1; one step = one NLML+grad evaluation of every item',
+            'N': N_DATA, 'items_per_gpu': n_items, 'parallelism': 'candidate-shard x%d' % world,
+            'l2': 'working set %.1f GiB per step >> 126 MB L2 (inputs larger than L2)' % (n_items * 2 * 2048 * 2048 * 8 / 2 ** 30)}
+
+
+def sample_indices(n_items, count):
+    """Stratified sample of the item list: `count` indices evenly spread over all items (every kernel family and every
+    restart draw is represented), the same in every process."""
+    count = max(1, min(count, n_items))
+    return [int(i) for i in np.linspace(0, n_items - 1, count).round()]
 
 
 def build_items(seed_offset=0, n_kernels=N_KERNELS, n_restarts=N_RESTARTS, n=N_DATA):
@@ -100,77 +121,249 @@ def fp64_peak():
         return 36.9, 'fallback: 36.9 TFLOP/s DMMA measured earlier on this pool'
 
 
-def cpu_reference_rate(X, y, items, thetas, noises, budget_s, max_items):
-    """NLML+grad evaluations / s of the CPU oracle (all BLAS threads), sequential over items like
-    ModelSelector._evaluate_models (src/autoks/core/model_selection/base.py:330)."""
+def host_cores():
+    return len(os.sched_getaffinity(0))
+
+
+def cpu_reference_rate(X, y, items, thetas, noises, budget_s, indices):
+    """Variant A: NLML+grad evaluations / s of the CPU oracle, sequential over items like
+    ModelSelector._evaluate_models (src/autoks/core/model_selection/base.py:330), every BLAS thread on each item.
+    Items that raise LinAlgError are not counted as completed."""
     from oracle import gp as ogp
     from oracle.adapter import to_oracle_expr
-    ncpu = len(os.sched_getaffinity(0))
+    ncpu = host_cores()
     try:        # torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host core it can use
         from threadpoolctl import threadpool_info, threadpool_limits
         threadpool_limits(limits=ncpu)
         cores = max([p.get('num_threads', 1) for p in threadpool_info()] or [1])
     except Exception:
         cores = ncpu
-    done, t0 = 0, time.time()
-    for i in range(min(max_items, len(items))):
+    done, failed, t0 = 0, 0, time.time()
+    for i in indices:
         try:
             ogp.lml_and_grad(to_oracle_expr(items[i]), thetas[i], noises[i], X, y)
+            done += 1
         except np.linalg.LinAlgError:
-            pass
-        done += 1
+            failed += 1
         if time.time() - t0 > budget_s:
             break
     dt = time.time() - t0
-    return done / dt, cores, done, dt
+    return done / dt, cores, done, failed, dt
 
 
-def fit_rate(eng, X, y, items, n_candidates=N_KERNELS):
-    """Secondary figure: FULLY FITTED candidates / s (optimize_restarts with 3 restarts, L-BFGS-B maxfun 1000) of the
-    whole C2 configuration (256 kernels), through the public scoring API (GPModel batch seam), BOMS hyperpriors."""
+_POOL_STATE = {}
+
+
+def _pool_init(X, y, exprs, thetas, noises):
+    try:
+        from threadpoolctl import threadpool_limits
+        _POOL_STATE['limit'] = threadpool_limits(limits=1)      # one BLAS thread per worker
+    except Exception:
+        pass
+    _POOL_STATE.update(X=X, y=y, exprs=exprs, thetas=thetas, noises=noises)
+
+
+def _pool_eval(i):
+    from oracle import gp as ogp
+    st = _POOL_STATE
+    try:
+        ogp.lml_and_grad(st['exprs'][i], st['thetas'][i], st['noises'][i], st['X'], st['y'])
+        return 1
+    except np.linalg.LinAlgError:
+        return 0
+
+
+class CpuPool(object):
+    """Variant B, the strongest CPU baseline: a process pool with one candidate per core and one BLAS thread per process
+    (how the reference parallelises experiments: src/training/run_experiment_from_file.py:81-84)."""
+
+    def __init__(self, X, y, items, thetas, noises):
+        import multiprocessing as mp
+        from oracle.adapter import to_oracle_expr
+        self.cores = host_cores()
+        exprs = [to_oracle_expr(k) for k in items]
+        ctx = mp.get_context('fork' if 'torch' not in sys.modules else 'spawn')
+        os.environ['OMP_NUM_THREADS'] = '1'
+        self.pool = ctx.Pool(self.cores, initializer=_pool_init, initargs=(X, y, exprs, thetas, noises))
+
+    def rate(self, indices):
+        t0 = time.time()
+        done = sum(self.pool.map(_pool_eval, indices, chunksize=1))
+        dt = time.time() - t0
+        return done / dt, done, len(indices) - done, dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def _timed_collective(fn, world, device):
+    """Wall time of a host-driven, multi-rank leg: barrier + synchronize on both sides, MAX over ranks."""
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = fn()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return out, dt
+
+
+def fit_rate(eng, X, y, items, world, n_candidates=N_KERNELS):
+    """STRONG scaling leg 1: the whole C2 configuration FULLY FITTED (optimize_restarts with 3 restarts, L-BFGS-B maxfun
+    1000, BOMS hyperpriors) through the public scoring API; with N ranks the 256 candidates are sharded (LPT on an a-priori
+    cost) and the records all-gathered, every rank ends with all 256 scores."""
     from ms_project_b200 import fitness, workloads
     from ms_project_b200.covariance import Covariance
-    from ms_project_b200.gp_model import GPModel, score_models
+    from ms_project_b200.gp_model import GPModel
     from ms_project_b200.gp_models import gp_regression
+    from ms_project_b200.parallel import score_models_sharded
     kernels = [items[3 * i].copy() for i in range(n_candidates)]
     models = [GPModel(Covariance(k)) for k in kernels]
     md = gp_regression(likelihood_hyperprior={'variance': workloads.boms_hyperpriors()['GP']['variance']})
     np.random.seed(0)
-    t0 = time.perf_counter()
-    scores = score_models(models, X, y, fitness.negative_bic, n_restarts=N_RESTARTS, engine=eng, model_dict=md)
-    dt = time.perf_counter() - t0
+    scores, dt = _timed_collective(lambda: score_models_sharded(models, X, y, fitness.negative_bic, n_restarts=N_RESTARTS,
+                                                                engine=eng, model_dict=md), world, eng.device)
     evals = sum(m.fit_result.n_evals for m in models)
-    return {'candidates': n_candidates, 'restarts': N_RESTARTS, 'seconds': dt, 'candidates_per_s': n_candidates / dt,
-            'nlml_grad_evaluations': int(evals), 'evaluations_per_s': evals / dt,
+    return {'config': 'C2 fitted: 256 candidates x 3 restarts, N=2048, L-BFGS-B maxfun 1000; total work fixed, sharded over the ranks',
+            'scaling': 'strong', 'n_gpus': world, 'candidates': n_candidates, 'restarts': N_RESTARTS, 'seconds': dt,
+            'candidates_per_s': n_candidates / dt, 'nlml_grad_evaluations': int(evals), 'evaluations_per_s': evals / dt,
             'failed': int(sum(m.failed_fitting for m in models)), 'best_nbic': float(np.nanmax(scores))}
 
 
+def strong_c4(eng, world, rank):
+    """STRONG scaling leg 2: one generation of configuration C4 (512 candidates, N = 4096, D = 8) sharded over the ranks:
+    (i) one NLML+grad evaluation of the whole population, (ii) a 3-restart fit with max_iters = C4_MAX_ITERS."""
+    import torch
+    import torch.distributed as dist
+    from ms_project_b200 import fitness, workloads
+    from ms_project_b200.covariance import Covariance
+    from ms_project_b200.gp_model import GPModel
+    from ms_project_b200.gp_models import gp_regression
+    from ms_project_b200.parallel import score_models_sharded, lpt_assign
+    from ms_project_b200.gp_model import model_cost
+    from ms_project_b200.program import ProgramBatch
+    X, Y, kernels = workloads.config_c4()
+    n = len(kernels)
+    owner = lpt_assign([model_cost(k, X.shape[0]) for k in kernels], world)
+    mine = [i for i in range(n) if owner[i] == rank]
+    batch = ProgramBatch([kernels[i] for i in mine])
+    slots = eng.slots_for(X.shape[0], X.shape[1], batch.n_items, batch.max_params, mem_fraction=0.8,
+                          extra_bytes=0 if eng._ws is None else eng._ws.numel())
+    eng.bind(X, Y, slots, batch.max_params)
+    eng.upload_programs(batch)
+    rng = np.random.default_rng(0)
+    thetas = [np.exp(0.3 * rng.standard_normal(int(k.size))) for k in kernels]
+    theta = batch.pack_theta([thetas[i] for i in mine], np.full(len(mine), 0.1))
+    gathered = torch.empty(world * ((n + world - 1) // world + 64), dtype=torch.float64, device=eng.device)
+
+    def eval_step():
+        out = eng.lml_grad(batch, theta)
+        if world > 1:
+            pad = torch.zeros(gathered.numel() // world, dtype=torch.float64, device=eng.device)
+            pad[:len(mine)] = batch.d_out[:len(mine)]
+            dist.all_gather_into_tensor(gathered, pad)
+        return out
+    eval_step()
+    out, dt_eval = _timed_collective(eval_step, world, eng.device)
+    status = np.asarray(out[2])[:len(mine)]
+    models = [GPModel(Covariance(k.copy())) for k in kernels]
+    md = gp_regression(likelihood_hyperprior={'variance': workloads.boms_hyperpriors()['GP']['variance']})
+    np.random.seed(1)
+    scores, dt_fit = _timed_collective(lambda: score_models_sharded(models, X, Y, fitness.log_likelihood_normalized, n_restarts=3,
+                                                                    engine=eng, model_dict=md, max_iters=C4_MAX_ITERS),
+                                       world, eng.device)
+    evals = sum(m.fit_result.n_evals for m in models)
+    N = float(X.shape[0])
+    return {'config': 'C4 evalg generation: 512 candidates, N=4096, D=8; total work fixed, sharded over the ranks (LPT)',
+            'scaling': 'strong', 'n_gpus': world, 'candidates': n,
+            'eval_step_seconds': dt_eval, 'eval_step_evaluations_per_s': n / dt_eval, 'eval_step_fp64_tflops': n * N ** 3 / dt_eval / 1e12,
+            'eval_status_counts_rank0': np.bincount(status, minlength=4).tolist(),
+            'fit_restarts': 3, 'fit_max_iters': C4_MAX_ITERS, 'fit_seconds': dt_fit, 'fit_candidates_per_s': n / dt_fit,
+            'fit_nlml_grad_evaluations': int(evals), 'fit_evaluations_per_s': evals / dt_fit,
+            'fit_failed': int(sum(m.failed_fitting for m in models)), 'fit_best_loglikn': float(np.nanmax(scores))}
+
+
+def c5_potrf(eng):
+    """The north star's C5 figure, driver-visible: blocked FP64 DMMA Cholesky of the N = 16384 K_y (SE_1*PER_1 + RQ_2, D = 2),
+    timed by CUDA events around the factorisation inside the library."""
+    import torch
+    from ms_project_b200 import workloads, _lib
+    from ms_project_b200.program import ProgramBatch
+    X, Y, k, noise = workloads.config_c5()
+    n = X.shape[0]
+    batch = ProgramBatch([k])
+    eng.bind(X, Y, 1, batch.max_params)
+    eng.upload_programs(batch)
+    theta = batch.pack_theta([k.param_array], [noise])
+    batch.h_theta.numpy()[:] = theta
+    batch.d_theta.copy_(batch.h_theta)
+    K0 = torch.empty((n, n), dtype=torch.float64, device=eng.device)
+    rc = eng.lib.b200gp_build_K(eng.ctx, batch.d_tokens.data_ptr(), batch.d_prog_off.data_ptr(), batch.d_theta.data_ptr(),
+                                batch.d_theta_off.data_ptr(), batch.d_all_ids.data_ptr(), 1, 1, K0.data_ptr())
+    _lib.check(eng.ctx, rc, 'b200gp_build_K')
+    K = torch.empty_like(K0)
+    eng.set_profiling(True)
+    ms, ld, st = [], 0.0, 0
+    for _ in range(4):
+        K.copy_(K0)
+        torch.cuda.synchronize()
+        ld, st = eng.potrf(K)
+        ms.append(eng.last_phase_ms()[0])
+    t0 = time.perf_counter()
+    lml, _g, st2, _t = eng.lml_grad(batch, theta)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    eng.set_profiling(False)
+    peak, _ = fp64_peak()
+    best = min(ms[1:])
+    return {'config': 'C5: N=16384, D=2, SE_1*PER_1+RQ_2', 'potrf_ms': best, 'potrf_fp64_tflops': float(n) ** 3 / 3 / (best * 1e-3) / 1e12,
+            'potrf_frac_of_dmma_peak': float(n) ** 3 / 3 / (best * 1e-3) / 1e12 / peak, 'logdet': float(ld), 'status': int(st),
+            'lml_grad_seconds': dt, 'lml_grad_fp64_tflops': float(n) ** 3 / dt / 1e12, 'lml': float(lml[0]), 'lml_status': int(st2[0])}
+
+
 def run_reference(args, rank, world):
+    """The reference's CPU path on ALL host cores of the box, whatever N is (rank 0 alone; the other ranks exit): every step
+    pool-evaluates one stratified sample of the 768 items, one candidate per core, BLAS threads = 1."""
     if rank != 0:
         return
     X, y, items, thetas, noises = build_items()
-    per_step = 4
-    # warm-up + timed steps, each a bounded sample of the same workload
+    pool = CpuPool(X, y, items, thetas, noises)
+    per_step = pool.cores
+    n_steps = args.warmup + args.steps
+    idx = sample_indices(len(items), per_step * n_steps)
     for w in range(args.warmup):
-        cpu_reference_rate(X, y, items[w:], thetas[w:], noises[w:], 1e9, 1)
+        pool.rate(idx[w::n_steps])
     t0 = time.time()
-    n_done = 0
-    cores = 1
-    for s in range(args.steps):
-        lo = (s * per_step) % len(items)
-        _, cores, d, _ = cpu_reference_rate(X, y, items[lo:], thetas[lo:], noises[lo:], 1e9, per_step)
+    n_done = n_failed = 0
+    for st in range(args.warmup, n_steps):
+        _, d, f, _ = pool.rate(idx[st::n_steps])
         n_done += d
+        n_failed += f
     dt = time.time() - t0
+    pool.close()
     val = n_done / dt
+    # variant A beside it: sequential over items, every BLAS thread on each
+    rate_a, cores_a, done_a, failed_a, dt_a = cpu_reference_rate(X, y, items, thetas, noises, 10.0, sample_indices(len(items), 12))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dt / max(args.steps, 1) * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'C2: 256 random CKS-grammar kernels x 3 restart draws, N=2048, D=1; NLML+grad per item',
-                   'N': N_DATA, 'items': len(items)},
-        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '%d items per step x %d steps of the C2 item list, sequential, NumPy/SciPy-LAPACK oracle '
-                                   '(GPy fork not installable; oracle restates its algorithm)' % (per_step, args.steps)},
+        'config': shared_config(args.gpus),
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': pool.cores, 'kind': 'port',
+                         'sample': 'process pool, one candidate per core, BLAS threads = 1 (variant B): %d items per step x %d steps, a '
+                                   'stratified sample (evenly spaced indices) of the 768 C2 items, %d evaluated, %d not PD; NumPy/SciPy-LAPACK '
+                                   'oracle (GPy fork not installable; the oracle restates its algorithm)'
+                                   % (per_step, args.steps, n_done, n_failed)},
+        'cpu_baseline_sequential': {'value': rate_a, 'unit': UNIT, 'cores': cores_a, 'kind': 'port',
+                                    'sample': 'sequential over %d evenly spaced items, all BLAS threads per item (variant A), %.1f s, %d not PD'
+                                              % (done_a, dt_a, failed_a)},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'fp64_tflops': val * N_DATA ** 3 / 1e12,
     }
@@ -274,40 +467,70 @@ def run_ours(args, rank, world, local_rank):
     except Exception:
         pass
 
+    # ---- legs every rank takes part in (collectives inside): the strong-scaling fits; their workspaces replace the headline's
+    fit = None if args.no_fit else fit_rate(eng, X, y, items, world)
+    c4 = None if args.no_fit else strong_c4(eng, world, rank)
+
     if rank == 0:
         total_items = world * n_items
         value = total_items * args.steps / (ms_max * 1e-3)
+        flops_item = float(N_DATA) ** 3 / 3.0
+
+        def phase(ms_, flops, kernels):
+            tf = chunk_items * flops / (ms_ * 1e-3) / 1e12
+            return {'ms': ms_, 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak, 'kernels': kernels}
+        step_ms = ms_max / args.steps
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': 'C2: 256 random CKS-grammar kernels x 3 restart draws = 768 (kernel, theta) items per GPU, '
-                                   'N=2048, D=1; one step = one NLML+grad evaluation of every item',
-                       'N': N_DATA, 'items_per_gpu': n_items, 'slots': slots, 'parallelism': 'candidate-shard x%d' % world,
-                       'l2': 'working set %.1f GiB per step >> 126 MB L2 (inputs larger than L2)' % (n_items * 2 * 2048 * 2048 * 8 / 2 ** 30)},
+            'config': shared_config(world),
+            'details': {'slots': slots, 'tma': 'TMA-fed DMMA tile GEMMs (UTMALDG + mbarrier ring); cp.async kernels when the tensor maps cannot be encoded'},
             'fp64_tflops': value * float(N_DATA) ** 3 / 1e12,
             'e2e': {'value': total_items * args.steps / e2e_s, 'unit': UNIT,
-                    'h2d_bytes_per_step': int(theta.nbytes), 'd2h_bytes_per_step': int(batch.h_out.numel() * 8 + batch.h_int.numel() * 4)},
+                    'h2d_bytes_per_step': int(theta.nbytes), 'd2h_bytes_per_step': int(batch.h_out.numel() * 8 + batch.h_int.numel() * 4),
+                    'api': 'Engine.lml_grad (host numpy theta in, host LML / gradients / status out); the fully fitted rate through '
+                           'GPModel / score_models is the `fit` object'},
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
             'roofline': {'bound': 'tensor', 'achieved': kinv_tflops, 'peak': peak, 'unit': 'TFLOP/s', 'frac': kinv_tflops / peak,
                          'traffic': traffic, 'traffic_note': traffic_note, 'algorithmic_bytes': 8.0 * N_DATA ** 2 * chunk_items,
-                         'kernel': 'kinv64_kernel (FP64 DMMA tile GEMM on 64 x 64 CTA tiles, K^-1 = V V^T; 1 launch per step)',
+                         'kernel': 'kinv64 kernel (FP64 DMMA tile GEMM on 64 x 64 CTA tiles, K^-1 = V V^T; 1 launch per step)',
                          'algorithmic': 'N^3/3 flops per item x %d items per launch' % chunk_items,
                          'launch_ms': phases[4], 'peak_source': peak_src},
-            'roofline_dmma_phases': {'achieved': dmma_tflops, 'peak': peak, 'unit': 'TFLOP/s', 'frac': dmma_tflops / peak,
-                                     'kernels': 'chol_update64/chol_trsm/potrf_diag + inv_update64/inv_trsm + kinv64 (Cholesky, L^-T, K^-1)',
-                                     'algorithmic': 'N^3 flops per item', 'ms': dmma_ms},
+            # every DMMA phase and the whole step against the same peak (not only the best kernel)
+            'roofline_phases': {
+                'cholesky': phase(phases[1], flops_item, 'potrf_diag + trsm + chol_update64 (right-looking blocked Cholesky)'),
+                'inverse': phase(phases[2], flops_item, 'trsm + inv_update64 (L^-T)'),
+                'kinv': phase(phases[4], flops_item, 'kinv64 (K^-1 = V V^T)'),
+                'dmma_phases': phase(dmma_ms, 3 * flops_item, 'the three above, N^3 flops per item'),
+                'step': {'ms': step_ms, 'achieved': value / world * float(N_DATA) ** 3 / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
+                         'frac': value / world * float(N_DATA) ** 3 / 1e12 / peak,
+                         'kernels': 'whole NLML+grad step per GPU incl. K-build, solves, gradient pass: N^3 algorithmic flops per item'}},
             'phases_ms': {'build_K': phases[0], 'cholesky': phases[1], 'inverse': phases[2], 'solve': phases[3],
                           'Kinv': phases[4], 'grad': phases[5], 'items': chunk_items},
             'status_counts': np.bincount(status, minlength=4).tolist(),
         }
+        if fit is not None:
+            line['fit'] = fit
+            line['strong_c4'] = c4
         if world == 1 and not args.no_fit:
-            line['fit'] = fit_rate(eng, X, y, items)
+            line['c5'] = c5_potrf(eng)
         if world == 1 and not args.no_cpu:
-            rate, cores, done, dt = cpu_reference_rate(X, y, items, thetas, noises, budget_s=20.0, max_items=64)
-            line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                    'sample': 'first %d of the 768 items, sequential, %.1f s (NumPy/SciPy-LAPACK oracle)' % (done, dt)}
+            # the CPU baselines on this box's host cores, on a stratified sample of the SAME item list:
+            # B = process pool, one candidate per core, BLAS threads 1 (the strongest); A = sequential, all BLAS threads per item
+            pool = CpuPool(X, y, items, thetas, noises)
+            idx = sample_indices(n_items, 3 * pool.cores)
+            pool.rate(idx[:pool.cores])                    # warm the workers
+            rate_b, done_b, failed_b, dt_b = pool.rate(idx[pool.cores:])
+            pool.close()
+            line['cpu_baseline'] = {'value': rate_b, 'unit': UNIT, 'cores': pool.cores, 'kind': 'port',
+                                    'sample': 'process pool, one candidate per core, BLAS threads = 1: %d evenly spaced items of the 768, '
+                                              '%.1f s, %d not PD (NumPy/SciPy-LAPACK oracle)' % (done_b, dt_b, failed_b)}
+            rate_a, cores_a, done_a, failed_a, dt_a = cpu_reference_rate(X, y, items, thetas, noises, 12.0, sample_indices(n_items, 16))
+            line['cpu_baseline_sequential'] = {'value': rate_a, 'unit': UNIT, 'cores': cores_a, 'kind': 'port',
+                                               'sample': 'sequential over %d evenly spaced items, all BLAS threads per item, %.1f s, %d not PD'
+                                                         % (done_a, dt_a, failed_a)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

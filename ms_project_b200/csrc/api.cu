@@ -1,6 +1,7 @@
 // C-ABI of libb200gp (include/b200gp.h): context, workspace carving, phase orchestration, jitter ladder.
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -51,6 +52,10 @@ struct b200gp_ctx {
   int gemm64 = 1;               // Cholesky / L^-T updates on 64 x 64 CTA tiles
   bool kinv64 = true;           // K^-1 on 64 x 64 CTA tiles with CTA-granular skipping (kinv64_kernel) instead of kinv_kernel
   bool fused_grad = false;      // K^-1 and the gradient of the <= 4-leaf programs in one kernel (kinv_grad_kernel)
+  int tma = 3;                  // 64 x 64 tile GEMMs fed by the TMA (1 + swizzle mode, tile_gemm64_tma.cuh); 0: cp.async
+  bool tma_ok = false;          // tensor maps of the bound workspace are valid
+  alignas(64) unsigned char tmaps[256];        // TmaMaps of the bound M1 / M2
+  alignas(64) unsigned char tmaps_potrf[256];  // TmaMaps of the matrix of the running b200gp_potrf call
   int n_groups = 2;             // slot groups (streams) of the batched schedule (measured at 256 x N=2048: 1 group 89.2 ms,
                                 // 2 / 3 / 4 groups 87.8 ms -- the schedule is not the limiter)
   cudaStream_t gstream[4]{};    // streams of the groups 1..3 (group 0 runs on the context stream)
@@ -155,6 +160,7 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
   if (configure_kernels() != 0 || configure_hellinger_kernels() != 0 || configure_predict_kernels() != 0 ||
       configure_align_kernels() != 0) return -5;
   b200gp_ctx* c = new b200gp_ctx();
+  if (const char* e = getenv("B200GP_TMA")) { const int v = atoi(e); if (v >= 0 && v <= 4) c->tma = v; }   // default override
   c->device = device;
   c->stream = static_cast<cudaStream_t>(cuda_stream);
   for (auto& e : c->ev) cudaEventCreate(&e);
@@ -223,6 +229,26 @@ int b200gp_set_tile64(b200gp_ctx* c, int enabled) {
   return 0;
 }
 
+static void encode_bound_maps(b200gp_ctx* c) {
+  c->tma_ok = false;
+  c->base.tma = 0;
+  c->base.tmaps = nullptr;
+  if (!c->bound || c->tma == 0) return;
+  if (tma_maps_bytes() > sizeof c->tmaps) return;
+  const Batch& b = c->base;
+  if (tma_encode_maps(c->tmaps, b.M1, b.M2, b.Np, (size_t)c->slots * b.Np, (c->tma == 4 ? 3 : c->tma) - 1) != 0) return;
+  c->tma_ok = true;
+  c->base.tma = c->tma;
+  c->base.tmaps = c->tmaps;
+}
+
+int b200gp_set_tma(b200gp_ctx* c, int mode) {
+  if (!c || mode < 0 || mode > 4) return -1;
+  c->tma = mode;
+  encode_bound_maps(c);
+  return 0;
+}
+
 int b200gp_set_fused_grad(b200gp_ctx* c, int enabled) {
   if (!c) return -1;
   c->fused_grad = enabled != 0;
@@ -288,6 +314,7 @@ int b200gp_bind(b200gp_ctx* c, void* ws, size_t ws_bytes, int slots, int max_par
   if (c->h_diag) cudaFreeHost(c->h_diag);
   CUCHECK(c, cudaMallocHost(&c->h_diag, cap * b.T * sizeof(double)));
   c->bound = true;
+  encode_bound_maps(c);       // needs c->bound; b.tma / b.tmaps stay 0 / null when the driver cannot encode (cp.async path)
   return 0;
 }
 
@@ -630,6 +657,11 @@ int b200gp_potrf(b200gp_ctx* c, double* dA, int N, void* work, double* logdet, i
   b.N = N; b.Np = N; b.T = T; b.D = 0; b.nslots = 1; b.mstride = (size_t)N * N;
   b.M1 = dA; b.M2 = nullptr;
   b.gemm64 = c->gemm64;
+  if (c->tma != 0 && tma_maps_bytes() <= sizeof c->tmaps_potrf &&
+      tma_encode_maps(c->tmaps_potrf, dA, nullptr, N, (size_t)N, (c->tma == 4 ? 3 : c->tma) - 1) == 0) {
+    b.tma = c->tma;
+    b.tmaps = c->tmaps_potrf;
+  }
   b.Dinv = cv.take<double>((size_t)T * NB * NB);
   b.logdet_part = cv.take<double>(T);
   b.slot_status = cv.take<int>(1);

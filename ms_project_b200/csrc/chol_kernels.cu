@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 #include "gemm_body.cuh"
 #include "tile_gemm64.cuh"
+#include "tile_gemm64_tma.cuh"
 #include "tile_potrf_blocked.cuh"
 
 namespace b200gp {
@@ -221,9 +222,135 @@ __global__ void __launch_bounds__(K64_THREADS, 3) trsm64_kernel(Batch b, int ste
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same three tile GEMMs with TMA-fed operands (tile_gemm64_tma.cuh).  The tensor maps describe M1 / M2 as one
+// (slots x Np) x Np matrix each, so a slot is a row offset.
+// ------------------------------------------------------------------------------------------------
+struct TmaMaps { CUtensorMap m1, m2; };
+size_t tma_maps_bytes() { return sizeof(TmaMaps); }
+
+template <int SW, int ST, int MINB>
+__global__ void __launch_bounds__(K64_THREADS, MINB) kinv64_tma_kernel(Batch b, const __grid_constant__ CUtensorMap mapV) {
+  const int slot = b.slot0 + blockIdx.y;
+  if (b.slot_status[slot] != 0) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int I, J;
+  tri_decode(blockIdx.x, I, J);
+  const size_t ld = b.Np;
+  double acc[TG_MT][TG_NT][2];
+  tile64_init(acc, nullptr, ld, 0.0);
+  tile64_pipeline_tma<SW, ST>(acc, &mapV, I * K64_T, slot * b.Np + I * K64_T, &mapV, I * K64_T, slot * b.Np + J * K64_T,
+                          (b.Np - I * K64_T) / TG_KC, smem_raw);
+  tile64_store(acc, tile64_cw(b.M1 + slot * b.mstride + (size_t)(I * K64_T) * ld + J * K64_T, ld), ld, 1.0);
+}
+
+template <int SW, int ST, int MINB>
+__global__ void __launch_bounds__(K64_THREADS, MINB) chol_update64_tma_kernel(Batch b, UpdRange upd,
+                                                                           const __grid_constant__ CUtensorMap mapL) {
+  const int slot = b.slot0 + blockIdx.y;
+  if (b.slot_status[slot] != 0) return;
+  const int bx = blockIdx.x >> 2, vi = (blockIdx.x >> 1) & 1, vj = blockIdx.x & 1;
+  int i, j;
+  if (upd.j1 >= b.T) {
+    int r, c;
+    tri_decode(bx, r, c);
+    i = upd.j0 + r; j = upd.j0 + c;
+  } else {
+    int rem = bx;
+    j = upd.j0;
+    while (rem >= b.T - j) { rem -= b.T - j; j++; }
+    i = j + rem;
+  }
+  if (i == j && vj > vi) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t ld = b.Np;
+  double* M1 = b.M1 + slot * b.mstride;
+  const int ri = i * NB + vi * K64_T, rj = j * NB + vj * K64_T;
+  double* Cw = tile64_cw(M1 + (size_t)ri * ld + rj, ld);
+  double acc[TG_MT][TG_NT][2];
+  tile64_init(acc, Cw, ld, -1.0);
+  tile64_pipeline_tma<SW, ST>(acc, &mapL, upd.k0 * NB, slot * b.Np + ri, &mapL, upd.k0 * NB, slot * b.Np + rj,
+                          upd.kw * (NB / TG_KC), smem_raw);
+  tile64_store(acc, Cw, ld, -1.0);
+}
+
+template <int SW, int ST, int MINB>
+__global__ void __launch_bounds__(K64_THREADS, MINB) inv_update64_tma_kernel(Batch b, UpdRange upd,
+                                                                          const __grid_constant__ CUtensorMap mapL,
+                                                                          const __grid_constant__ CUtensorMap mapV) {
+  const int slot = b.slot0 + blockIdx.y;
+  if (b.slot_status[slot] != 0) return;
+  const int bx = blockIdx.x >> 2, vi = (blockIdx.x >> 1) & 1, vj = blockIdx.x & 1;
+  const int J = upd.k0 + upd.kw;
+  const int m = upd.j0 + bx / J, j = bx % J;
+  const int kb = j > upd.k0 ? j : upd.k0;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t ld = b.Np;
+  double* M2 = b.M2 + slot * b.mstride;
+  const int rj = j * NB + vi * K64_T, rm = m * NB + vj * K64_T;
+  const int kskip = (kb == j && vi == 1) ? K64_T : 0;
+  double* Cw = tile64_cw(M2 + (size_t)rj * ld + rm, ld);
+  double acc[TG_MT][TG_NT][2];
+  tile64_init(acc, Cw, ld, (j >= upd.k0) ? 0.0 : 1.0);
+  tile64_pipeline_tma<SW, ST>(acc, &mapV, kb * NB + kskip, slot * b.Np + rj, &mapL, kb * NB + kskip, slot * b.Np + rm,
+                          ((J - kb) * NB - kskip) / TG_KC, smem_raw);
+  tile64_store(acc, Cw, ld, 1.0);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (libcuda is not linked)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int tma_encode_maps(void* out, double* M1, double* M2, int Np, size_t rows, int sw) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess)
+      return -1;
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  TmaMaps* maps = static_cast<TmaMaps*>(out);
+  const CUtensorMapSwizzle mode = sw == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : sw == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                                                          : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const cuuint64_t dims[2] = {(cuuint64_t)Np, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)Np * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)TG_KC, (cuuint32_t)K64_T};
+  const cuuint32_t estr[2] = {1, 1};
+  double* ptrs[2] = {M1, M2};
+  CUtensorMap* dst[2] = {&maps->m1, &maps->m2};
+  for (int q = 0; q < 2; q++) {
+    if (!ptrs[q]) continue;
+    const CUresult r = encode(dst[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ptrs[q], dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, mode, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return (int)r;
+  }
+  return 0;
+}
+
+// b.tma: 1 / 2 / 3 = swizzle none / 128B / 128B_ATOM_32B with a 4-stage ring and three CTAs per SM; 4 = 128B_ATOM_32B with a
+// 3-stage ring and FOUR CTAs per SM (the TMA kernels need <= 128 registers)
+#define TMA_DISPATCH(b, CALL)                          \
+  switch ((b).tma) {                                   \
+    case 1: CALL(0, 4, 3); break;                      \
+    case 2: CALL(1, 4, 3); break;                      \
+    case 4: CALL(2, 3, 4); break;                      \
+    default: CALL(2, 4, 3); break;                     \
+  }
+
 void launch_kinv64(const Batch& b, cudaStream_t s) {
   dim3 grid(tri_count(2 * b.T), b.nslots);
-  kinv64_kernel<<<grid, K64_THREADS, K64_SMEM_BYTES, s>>>(b);
+  if (b.tma && b.tmaps) {
+    const TmaMaps& tm = *static_cast<const TmaMaps*>(b.tmaps);
+#define CALL(SW, ST, MB) kinv64_tma_kernel<SW, ST, MB><<<grid, K64_THREADS, k64t_smem_bytes(ST), s>>>(b, tm.m2)
+    TMA_DISPATCH(b, CALL)
+#undef CALL
+  } else {
+    kinv64_kernel<<<grid, K64_THREADS, K64_SMEM_BYTES, s>>>(b);
+  }
   g_launch_count++;
 }
 
@@ -261,7 +388,14 @@ void launch_vupdate(const Batch& b, UpdRange r, cudaStream_t s) {
   if (ntiles <= 0 || r.kw <= 0) return;
   if (b.gemm64) {
     dim3 grid(4 * ntiles, b.nslots);
-    inv_update64_kernel<<<grid, K64_THREADS, K64_SMEM_BYTES, s>>>(b, r);
+    if (b.tma && b.tmaps) {
+      const TmaMaps& tm = *static_cast<const TmaMaps*>(b.tmaps);
+#define CALL(SW, ST, MB) inv_update64_tma_kernel<SW, ST, MB><<<grid, K64_THREADS, k64t_smem_bytes(ST), s>>>(b, r, tm.m1, tm.m2)
+      TMA_DISPATCH(b, CALL)
+#undef CALL
+    } else {
+      inv_update64_kernel<<<grid, K64_THREADS, K64_SMEM_BYTES, s>>>(b, r);
+    }
   } else {
     dim3 grid(2 * ntiles, b.nslots);
     inv_update_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, r);
@@ -275,7 +409,14 @@ void launch_update(const Batch& b, UpdRange r, cudaStream_t s) {
   if (ntiles <= 0 || r.kw <= 0) return;
   if (b.gemm64) {
     dim3 grid(4 * ntiles, b.nslots);
-    chol_update64_kernel<<<grid, K64_THREADS, K64_SMEM_BYTES, s>>>(b, r);
+    if (b.tma && b.tmaps) {
+      const TmaMaps& tm = *static_cast<const TmaMaps*>(b.tmaps);
+#define CALL(SW, ST, MB) chol_update64_tma_kernel<SW, ST, MB><<<grid, K64_THREADS, k64t_smem_bytes(ST), s>>>(b, r, tm.m1)
+      TMA_DISPATCH(b, CALL)
+#undef CALL
+    } else {
+      chol_update64_kernel<<<grid, K64_THREADS, K64_SMEM_BYTES, s>>>(b, r);
+    }
   } else {
     dim3 grid(2 * ntiles, b.nslots);
     chol_update_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, s>>>(b, r);
@@ -377,6 +518,16 @@ int configure_chol_kernels() {
     e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, K64_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
   }
+#define SETATTR(K, SW, ST, MB)                                                                                              \
+  if ((e = cudaFuncSetAttribute((const void*)K<SW, ST, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, k64t_smem_bytes(ST))) != \
+      cudaSuccess)                                                                                                              \
+    return (int)e;
+#define SETALL(K) SETATTR(K, 0, 4, 3) SETATTR(K, 1, 4, 3) SETATTR(K, 2, 4, 3) SETATTR(K, 2, 3, 4)
+  SETALL(kinv64_tma_kernel)
+  SETALL(chol_update64_tma_kernel)
+  SETALL(inv_update64_tma_kernel)
+#undef SETALL
+#undef SETATTR
   return 0;
 }
 

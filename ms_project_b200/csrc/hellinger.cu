@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "kprog.cuh"
 #include "tile_potrf.cuh"
+#include "tile_potrf_small.cuh"
 
 namespace b200gp {
 
@@ -79,13 +80,18 @@ hellinger_precompute_kernel(const double* __restrict__ Xsub, int n, int D, const
   }
 }
 
-__global__ void __launch_bounds__(TP_THREADS, 1)
+// One CTA per (pair, sample): pivots of chol(1/2 (G_i,s + G_j,s)) by the two-columns-per-barrier register factorisation of
+// tile_potrf_small.cuh.  Only the lower triangle of the two Gram matrices is read; R block rows of 16 cover the order
+// (R = 7 for the 100-point subsets of C3: 28 doubles per thread, three CTAs per SM).  blockIdx.y = sample: every CTA in
+// flight works on the SAME sample, whose M Gram matrices (C3: 500 x 80 KB, half of it touched) stay resident in the
+// 126 MB L2 while all pairs of that sample are processed.
+template <int R, int MINB, int COLS>
+__global__ void __launch_bounds__(TS_THREADS, MINB)
 hellinger_pair_kernel(const double* __restrict__ logdet, const double* __restrict__ G, int S, int n,
                       const int* __restrict__ pair_i, const int* __restrict__ pair_j, double tol,
                       double* __restrict__ h, int* __restrict__ hstatus) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  TilePotrfSmem& T = *reinterpret_cast<TilePotrfSmem*>(smem_raw);
-  const int s = blockIdx.x, pr = blockIdx.y;
+  __shared__ SmallPotrfSmem<R> T;
+  const int pr = blockIdx.x, s = blockIdx.y;
   const int mi = pair_i[pr], mj = pair_j[pr];
   const double ldi = logdet[(size_t)mi * S + s], ldj = logdet[(size_t)mj * S + s];
   double ldpq = ldi;
@@ -94,18 +100,28 @@ hellinger_pair_kernel(const double* __restrict__ logdet, const double* __restric
     const double* Gi = G + ((size_t)mi * S + s) * n * n;
     const double* Gj = G + ((size_t)mj * S + s) * n * n;
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    double a[TP_R][TP_R];
+    double a[R * (R + 1) / 2];
 #pragma unroll
-    for (int p = 0; p < TP_R; p++)
+    for (int p = 0; p < R; p++)
 #pragma unroll
-      for (int q = 0; q < TP_R; q++) {
+      for (int q = 0; q <= p; q++) {
         const int i = ty + 16 * p, c = tx + 16 * q;
         double v = (i == c) ? 1.0 : 0.0;
-        if (i < n && c < n) v = 0.5 * (Gi[(size_t)i * n + c] + Gj[(size_t)i * n + c]);
-        a[p][q] = v;
+        if (i < n && c <= i) v = 0.5 * (__ldg(Gi + (size_t)i * n + c) + __ldg(Gj + (size_t)i * n + c));
+        a[ts_idx(p, q)] = v;
       }
-    tile_potrf_pivots(a, T, n);
-    ldpq = logdet_from_pivots(T, n);
+    small_potrf_pivots<R, COLS>(a, T, n);
+    double sum = 0.0;                 // warp 0 sums log(piv[0..n)) in a fixed order
+    if (threadIdx.x < 32) {
+#pragma unroll
+      for (int r = 0; r < (16 * R + 31) / 32; r++) {
+        const int j = threadIdx.x + 32 * r;
+        if (j < n) sum += log(T.piv[j]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    ldpq = sum;
     bad = T.fail != 0;
   }
   if (threadIdx.x == 0) {
@@ -315,14 +331,15 @@ void launch_hellinger_precompute(const double* Xsub, int n, int D, const int4* p
 
 void launch_hellinger_pairs(const double* logdet, const double* G, int S, int n, const int* pair_i, const int* pair_j,
                             int npairs, double tol, double* h, int* hstatus, double* dist, int* status, cudaStream_t st) {
-  const int chunk = 32768;            // grid.y limit is 65535
-  for (int off = 0; off < npairs; off += chunk) {
-    const int m = npairs - off < chunk ? npairs - off : chunk;
-    dim3 grid(S, m);
-    hellinger_pair_kernel<<<grid, TP_THREADS, sizeof(TilePotrfSmem), st>>>(logdet, G, S, n, pair_i + off, pair_j + off, tol,
-                                                                          h + (size_t)off * S, hstatus + (size_t)off * S);
-    g_launch_count++;
-  }
+  dim3 grid(npairs, S);               // x = pair (fastest), y = sample: sample-major execution order, see the kernel
+#define HP_LAUNCH(R, MINB, COLS) hellinger_pair_kernel<R, MINB, COLS><<<grid, TS_THREADS, 0, st>>>(logdet, G, S, n, pair_i, pair_j, tol, h, hstatus)
+  // measured on C3 (124 750 pairs x 20 samples, n = 100): one column per barrier with three CTAs per SM 0.224 s, two columns
+  // per barrier with three CTAs (80 B of spills) 0.245 s, with two CTAs (no spills) 0.273 s; round 1's kernel 0.369 s
+  if (n <= 64) HP_LAUNCH(4, 4, 2);
+  else if (n <= 112) HP_LAUNCH(7, 3, 1);
+  else HP_LAUNCH(8, 2, 2);
+#undef HP_LAUNCH
+  g_launch_count++;
   hellinger_reduce_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(h, hstatus, S, npairs, dist, status);
   g_launch_count++;
 }

@@ -46,12 +46,21 @@ struct Batch {
   const double* lut;         // OP_LOOKUP distance matrix (lut_n x lut_n, b200gp_set_lookup) or null
   int lut_n;
   int gemm64;                // 1: Cholesky / L^-T updates on 64 x 64 CTA tiles (chol_update64 / inv_update64), 0: 128 x 64 tiles
+  int tma;                   // 0: the 64 x 64 tile GEMMs stage their operands with cp.async; 1 + SW: with the TMA (tile_gemm64_tma.cuh)
+                             // and swizzle mode SW (0 none, 1 128B, 2 128B_ATOM_32B) of the tensor maps below
+  const void* tmaps;         // host pointer: TmaMaps of this batch's M1 / M2 (launch-time only; kernels get the maps by value)
   // compiled programs of this chunk (cprog.cuh), written by launch_compile
   CProg* cprog;              // [slot]
   int* klist;                // [CK_KINDS][list_stride] slots of each kind, in slot order
   int* kcount;               // [CK_KINDS]
   int list_stride;
 };
+
+struct TmaMaps;             // chol_kernels.cu: CUtensorMap of M1 and of M2, rows = slots x Np, columns = Np
+// Encodes the tensor maps of a batch's M1 / M2 (M2 may be null) for swizzle mode `sw`; returns 0 or a CUresult / -1 when the
+// driver entry point is unavailable.  `out` must hold tma_maps_bytes() bytes, 64-byte aligned.
+int tma_encode_maps(void* out, double* M1, double* M2, int Np, size_t rows, int sw);
+size_t tma_maps_bytes();
 
 enum GemmMode : int { GM_TRSM = 0, GM_VTRSM = 3, GM_KINV = 4, GM_UPD = 5, GM_VUPD = 6 };
 

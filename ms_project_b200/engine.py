@@ -73,6 +73,11 @@ class Engine(object):
         """CTA tile shape of the DMMA phases: 64 x 64 (default) or 128 x 64; bit-identical results."""
         _lib.check(self.ctx, self.lib.b200gp_set_tile64(self.ctx, int(bool(on))), 'b200gp_set_tile64')
 
+    def set_tma(self, mode):
+        """Operand staging of the 64 x 64 tile GEMMs: 3 TMA + 32-byte-atom swizzle (default), 2 TMA + 128-byte swizzle,
+        1 TMA unswizzled, 0 cp.async; bit-identical results."""
+        _lib.check(self.ctx, self.lib.b200gp_set_tma(self.ctx, int(mode)), 'b200gp_set_tma')
+
     def set_fused_grad(self, on):
         """K^-1 fused with the gradient pass of the <= 4-leaf programs (one kernel, K^-1 never written to HBM)."""
         _lib.check(self.ctx, self.lib.b200gp_set_fused_grad(self.ctx, int(bool(on))), 'b200gp_set_fused_grad')

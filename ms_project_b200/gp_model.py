@@ -129,7 +129,7 @@ def _waves(models):
 
 
 def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engine=None, model_dict=None, overlap=None,
-                 comm=None):
+                 comm=None, max_iters=1000):
     """GPModel.score_model for a whole list in ONE lock-step GPU batch (same per-model results and side effects as
     calling score_model on each, including the retry-once rule and failed_fitting).
 
@@ -142,7 +142,7 @@ def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engi
     each rank fits its slice, one all_gather of fixed-width records writes scores and optimised parameters into EVERY
     rank's model objects.  Every rank draws the restart points of the WHOLE list and -- after the failure flags have been
     all-gathered -- the retry points of EVERY failing model, so np.random stays in the same state on all ranks and the search
-    loop continues identically everywhere."""
+    loop continues identically everywhere.  `max_iters` is paramz's optimiser budget (GPModel.fit leaves it at 1000)."""
     check_optimizer(optimizer)
     from .fit import draw_starts
     if not models:
@@ -171,9 +171,11 @@ def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engi
             engines = [engine, engine.peer()]
             for e in engines:
                 e.ensure_bound(x, y, (n_inst + 1) // 2, maxp)
-            return fit_models_overlapped(engines, ks, ls, num_restarts=n_restarts, robust=True, starts=st, optimizer=optimizer)
+            return fit_models_overlapped(engines, ks, ls, num_restarts=n_restarts, max_iters=max_iters, robust=True, starts=st,
+                                         optimizer=optimizer)
         engine.ensure_bound(x, y, n_inst, maxp)
-        return fit_models(engine, ks, ls, num_restarts=n_restarts, robust=True, starts=st, optimizer=optimizer)
+        return fit_models(engine, ks, ls, num_restarts=n_restarts, max_iters=max_iters, robust=True, starts=st,
+                          optimizer=optimizer)
 
     for w, wave in enumerate(_waves(models)):
         if w > 0:                       # restart 0 = the parameters the previous occurrence of the shared object left behind

@@ -8,6 +8,7 @@ loop logic as scipy's `_minimize_lbfgsb`, but hands control back whenever an obj
 hundreds of independent instances advance in lock-step against one batched GPU evaluation.
 tests/test_optimizer.py checks bit-identical trajectories against `fmin_l_bfgs_b`."""
 import numpy as np
+import scipy
 from scipy.optimize import _lbfgsb
 
 try:                                    # scipy >= 1.15 carries the ILP64 switch next to the driver
@@ -15,6 +16,21 @@ try:                                    # scipy >= 1.15 carries the ILP64 switch
 except Exception:                       # pragma: no cover
     _ILP64 = False
 _INT = np.int64 if _ILP64 else np.int32
+
+
+def _check_setulb():
+    """`setulb` is a PRIVATE scipy routine whose argument list changed with the C rewrite of L-BFGS-B (scipy 1.15: integer
+    task arrays, `ln_task`, no `iprint` / `csave`).  This module is written against that signature (tested with scipy
+    1.15 - 1.18); anything else fails HERE, at import, with a message -- not as a TypeError inside the first fit."""
+    doc = getattr(_lbfgsb.setulb, '__doc__', None) or ''
+    ver = tuple(int(p) for p in scipy.__version__.split('.')[:2] if p.isdigit())
+    if ver < (1, 15) or ('ln_task' not in doc and 'iprint' in doc):
+        raise ImportError('ms_project_b200.optimizer drives scipy.optimize._lbfgsb.setulb with the scipy >= 1.15 signature '
+                          '(m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task, lsave, isave, dsave, maxls, ln_task); '
+                          'found scipy %s with setulb%s' % (scipy.__version__, doc.splitlines()[0] if doc else ' (no signature)'))
+
+
+_check_setulb()
 
 
 class LBFGSB(object):

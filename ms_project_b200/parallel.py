@@ -132,7 +132,7 @@ class Comm(object):
 
 
 def score_models_sharded(models, x, y, scoring_func, optimizer=None, n_restarts=10, engine=None, model_dict=None,
-                         policy='lpt'):
+                         policy='lpt', max_iters=1000):
     """`gp_model.score_models` across all ranks: every rank holds the full candidate list, fits only its share, then the
     records are all-gathered and written into EVERY rank's model objects, so the search loop continues identically
     everywhere.  Restart draws are made for the whole list on every rank (same global seed => same draws as a single-GPU
@@ -140,7 +140,7 @@ def score_models_sharded(models, x, y, scoring_func, optimizer=None, n_restarts=
     optimisation and no device reduction depends on the batch composition."""
     from .gp_model import score_models
     return score_models(models, x, y, scoring_func, optimizer=optimizer, n_restarts=n_restarts, engine=engine,
-                        model_dict=model_dict, comm=Comm(policy) if world()[1] > 1 else None)
+                        model_dict=model_dict, comm=Comm(policy) if world()[1] > 1 else None, max_iters=max_iters)
 
 
 def hellinger_matrix_sharded(builder, active_models, n_models):

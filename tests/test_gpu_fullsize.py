@@ -93,3 +93,49 @@ def test_c5_size_cholesky_and_gradient_properties(engine):
     z = torch.linalg.solve_triangular(L, yd, upper=False)
     lml_ref = -0.5 * (n * np.log(2 * np.pi) + logdet + float((z * z).sum()))
     assert abs(lml[0] - lml_ref) <= 1e-8 * max(1.0, abs(lml_ref)), (lml[0], lml_ref)
+
+
+def test_c4_size_parity_every_kernel_family_of_programs(engine):
+    """C4 size (N = 4096, D = 8): one program for each device code path -- <= 4 leaves (poly_*<4>), 5-8 leaves
+    (poly_*<8>) and > 8 leaves (the interpreter) -- against the oracle at the north-star tolerances."""
+    from conftest import from_string
+    from ms_project_b200 import workloads
+    from ms_project_b200.program import ProgramBatch
+    from oracle import gp
+    X, y, _ = workloads.config_c4(n=4096, pop=1)
+    names = ['SE_1 * RQ_2 + SE_3 * SE_8',                                                          # 4 leaves
+             'SE_1 * RQ_2 + SE_3 * RQ_4 * SE_5 + RQ_6 + SE_7 * SE_8',                              # 8 leaves
+             'SE_1 + RQ_2 * SE_3 + SE_4 * RQ_5 + RQ_6 * SE_7 + SE_8 * SE_1 + RQ_3 + SE_5']         # 11 leaves: interpreter
+    kernels = [from_string(s) for s in names]
+    rng = np.random.RandomState(4)
+    batch = ProgramBatch(kernels)
+    engine.bind(X, y, slots=3, max_params=batch.max_params)
+    engine.upload_programs(batch)
+    ks = [np.exp(rng.uniform(-0.3, 0.7, size=int(p))) for p in batch.n_params]
+    nz = np.array([0.05, 0.1, 0.2])
+    lml, g, st, _ = [a.copy() for a in engine.lml_grad(batch, batch.pack_theta(ks, nz))]
+    assert (st == 0).all()
+    for i, k in enumerate(kernels):
+        ref, gref, _ = gp.lml_and_grad(to_oracle_expr(k), ks[i], nz[i], X, y)
+        a, b = batch.theta_off[i], batch.theta_off[i + 1]
+        assert abs(lml[i] - ref) <= 1e-8 * max(1.0, abs(ref)), (names[i], lml[i], ref)
+        assert np.max(np.abs(g[a:b] - gref)) <= 1e-6 * max(1.0, np.max(np.abs(gref))), (names[i], g[a:b], gref)
+
+
+def test_c5_kernel_against_the_oracle_at_n8192(engine):
+    """C5's kernel (SE_1 * PER_1 + RQ_2, D = 2, the look-ahead single-matrix schedule with wide panels: T = 64 > 32) against
+    the ORACLE's LML and gradient at N = 8192 (N = 16384 costs the CPU several minutes and 20 GB; the schedule and every
+    kernel are the same from T = 33 tile columns on)."""
+    from ms_project_b200 import workloads
+    from ms_project_b200.program import ProgramBatch
+    from oracle import gp
+    X, y, k, noise = workloads.config_c5(n=8192)
+    batch = ProgramBatch([k])
+    engine.bind(X, y, slots=1, max_params=batch.max_params)
+    engine.upload_programs(batch)
+    th = np.asarray(k.param_array, dtype=np.float64)
+    lml, g, st, _ = [a.copy() for a in engine.lml_grad(batch, batch.pack_theta([th], [noise]))]
+    assert st[0] == 0
+    ref, gref, _ = gp.lml_and_grad(to_oracle_expr(k), th, noise, X, y)
+    assert abs(lml[0] - ref) <= 1e-8 * max(1.0, abs(ref)), (lml[0], ref)
+    assert np.max(np.abs(g[:th.size + 1] - gref)) <= 1e-6 * max(1.0, np.max(np.abs(gref))), (g[:th.size + 1], gref)
