@@ -468,6 +468,8 @@ def run_ours(args, rank, world, local_rank):
         pass
 
     # ---- legs every rank takes part in (collectives inside): the strong-scaling fits; their workspaces replace the headline's
+    if not args.no_fit and rank != 0:        # the strong legs share ONE candidate list (rank 0's); the headline's differ per rank
+        X, y, items, _, _ = build_items(seed_offset=0)
     fit = None if args.no_fit else fit_rate(eng, X, y, items, world)
     c4 = None if args.no_fit else strong_c4(eng, world, rank)
 

@@ -13,6 +13,12 @@
 //     32 distinct banks per half warp -- conflict-free without padding.  SW = 1 (16-byte atoms, row & 7) and SW = 0 (none)
 //     exist for comparison.
 // Every output element still sums its products in ascending k: results are bit-identical to the cp.async kernels.
+// Measured on B200 (256 C2 items, N = 2048; tools/tma_probe.py): Cholesky + L^-T + K^-1 70.65 ms with cp.async, 72.6 with
+// unswizzled tensor maps (4-way bank conflicts), 69.5 with SWIZZLE_128B, 69.3 with SWIZZLE_128B_ATOM_32B (kept); a 3-stage
+// ring with four CTAs per SM 69.3-69.5 (no gain).  Tried on top and removed: letting a warp whose first chunks are
+// structurally zero (V_II / diagonal blocks) consume and release them without loading or issuing -- possible now that no
+// block barrier ties the warps -- 69.3 -> 69.7 ms: the pipe is already ~95 % busy on the long tiles, the skipped 2 % of DMMAs
+// do not pay for the extra control flow.
 #pragma once
 #include <cuda.h>
 #include "tile_gemm64.cuh"
