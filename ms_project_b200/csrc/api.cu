@@ -1,7 +1,6 @@
 // C-ABI of libb200gp (include/b200gp.h): context, workspace carving, phase orchestration, jitter ladder.
 #include <cmath>
 #include <cstdarg>
-#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -160,7 +159,6 @@ int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
   if (configure_kernels() != 0 || configure_hellinger_kernels() != 0 || configure_predict_kernels() != 0 ||
       configure_align_kernels() != 0) return -5;
   b200gp_ctx* c = new b200gp_ctx();
-  if (const char* e = getenv("B200GP_TMA")) { const int v = atoi(e); if (v >= 0 && v <= 4) c->tma = v; }   // default override
   c->device = device;
   c->stream = static_cast<cudaStream_t>(cuda_stream);
   for (auto& e : c->ev) cudaEventCreate(&e);
