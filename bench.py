@@ -458,12 +458,13 @@ def run_ours(args, rank, world, local_rank):
     dmma_tflops = chunk_items * float(N_DATA) ** 3 / (dmma_ms * 1e-3) / 1e12
     traffic, traffic_note = None, None
     try:
-        tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic_r01.json')))
+        cands = sorted(f for f in os.listdir(os.path.join(ROOT, 'profiles')) if f.startswith('ncu_traffic_') and f.endswith('.json'))
+        tr = json.load(open(os.path.join(ROOT, 'profiles', cands[-1])))            # the latest capture (r02... sorts after r01)
         per_item = (tr['kinv64_kernel']['dram_bytes_read'] + tr['kinv64_kernel']['dram_bytes_write']) / tr['items_per_launch']
         traffic = per_item * chunk_items
-        traffic_note = ('dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of kinv64_kernel at %d items per '
-                        'launch, scaled to the %d items of this launch (algorithmic: 8 N^2 bytes per item = read V upper + '
-                        'write K^-1 lower)' % (tr['items_per_launch'], chunk_items))
+        traffic_note = ('dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of the kinv64 kernel at %d items per '
+                        'launch (%s), scaled to the %d items of this launch (algorithmic: 8 N^2 bytes per item = read V upper + '
+                        'write K^-1 lower)' % (tr['items_per_launch'], cands[-1], chunk_items))
     except Exception:
         pass
 

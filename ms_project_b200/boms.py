@@ -28,9 +28,6 @@ def set_priors(param, priors, in_place=False):
 class KernelKernelGPModel(object):
     def __init__(self, kernel_kernel=None, noise_var=None, exact_f_eval=False, optimizer='lbfgsb', max_iters=1000,
                  optimize_restarts=5, verbose=True, kernel_kernel_hyperpriors=None):
-        if exact_f_eval:
-            raise NotImplementedError('exact_f_eval=True fixes the noise variance; fixed parameters are not implemented '
-                                      '(BayesOptGPStrategy uses exact_f_eval=False, bayes_opt_gp_strategy.py:29)')
         self.noise_var = noise_var
         self.exact_f_eval = exact_f_eval
         self.optimize_restarts = optimize_restarts
@@ -66,9 +63,14 @@ class KernelKernelGPModel(object):
                 set_priors(self.model.likelihood, self.kernel_hyperpriors['GP'], in_place=True)
             if 'SE' in self.kernel_hyperpriors:
                 set_priors(self.model.kern, self.kernel_hyperpriors['SE'], in_place=True)
-        # noise: positive (Logexp) -- the branch the reference takes when hyperpriors exist; its bounded Logistic
-        # alternative (no priors) is replaced by the same positive constraint here
-        self.model.Gaussian_noise.variance.constrain_positive(warning=False)
+        # gp_regression_models.py:93-102: exact evaluations fix the noise at 1e-6; otherwise the noise stays positive when the
+        # model carries priors (paramz has no log-Jacobian for Logistic) and is bounded to [1e-9, 1e6] when it does not
+        if self.exact_f_eval:
+            self.model.Gaussian_noise.constrain_fixed(1e-6, warning=False)
+        elif self.model.priors.size > 0:
+            self.model.Gaussian_noise.constrain_positive(warning=False)
+        else:
+            self.model.Gaussian_noise.constrain_bounded(1e-9, 1e6, warning=False)
 
     def update(self, x_all, y_all, x_new, y_new):
         """Update model with new observations (gp_regression_models.py:106-113)."""

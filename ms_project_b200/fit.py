@@ -13,7 +13,7 @@ L-BFGS-B step (scipy's `setulb`) is called per instance."""
 import numpy as np
 
 from .gpy_compat.priors import Gaussian as _GaussianPrior, LogGaussian as _LogGaussianPrior
-from .gpy_compat.transformations import Logexp
+from .gpy_compat.transformations import Logexp, Logistic, Fixed
 from .optimizer import make_optimizer
 from .program import ProgramBatch
 
@@ -58,6 +58,7 @@ class _PriorTable(object):
             self.mu[i], self.s2[i], self.const[i] = p.mu, p.sigma2, p.constant
         self.other = [(p, np.asarray(ix, dtype=int)) for p, ix in other.values()]
         self.has = self.kind != 0
+        self.jac = self.has.copy()       # priored parameters whose constraint has a log-Jacobian (Logexp)
         self.lg = self.kind == 1
         self.ga = self.kind == 2
 
@@ -79,11 +80,61 @@ class _PriorTable(object):
             for p, ix in self.other:
                 lp[ix] = p.lnpdf(theta[ix])
                 dlp[ix] = p.lnpdf_grad(theta[ix])
-            if self.has.any():
-                t = theta[self.has]
-                lp[self.has] += _LOGEXP.log_jacobian(t)
-                dlp[self.has] += _LOGEXP.log_jacobian_grad(t)
+            if self.jac.any():
+                t = theta[self.jac]
+                lp[self.jac] += _LOGEXP.log_jacobian(t)
+                dlp[self.jac] += _LOGEXP.log_jacobian_grad(t)
         return lp, dlp
+
+
+class _TransformTable(object):
+    """Flat per-parameter constraint description in device theta layout: Logexp (every parameter the grammar creates),
+    Logistic(lower, upper) (`constrain_bounded`) or fixed (`constrain_fixed`: the optimiser still carries the coordinate,
+    with a zero gradient, so it never moves and never influences the other coordinates' L-BFGS-B updates)."""
+
+    def __init__(self, transforms, values):
+        n = len(transforms)
+        self.kind = np.zeros(n, dtype=np.int8)          # 0 Logexp, 1 Logistic, 2 fixed
+        self.lo = np.zeros(n)
+        self.hi = np.ones(n)
+        self.fixed_value = np.asarray(values, dtype=np.float64).copy()
+        for i, t in enumerate(transforms):
+            if isinstance(t, Logistic):
+                self.kind[i], self.lo[i], self.hi[i] = 1, t.lower, t.upper
+            elif isinstance(t, Fixed):
+                self.kind[i] = 2
+            elif not isinstance(t, Logexp):
+                raise NotImplementedError('constraint %s is not supported on the scoring path' % type(t).__name__)
+        self.plain = not self.kind.any()
+        self.lg = self.kind == 1
+        self.fx = self.kind == 2
+
+    def f(self, x):
+        th = _LOGEXP.f(x)
+        if not self.plain:
+            if self.lg.any():
+                xx = np.clip(x[self.lg], -700.0, 700.0)
+                th[self.lg] = self.lo[self.lg] + (self.hi[self.lg] - self.lo[self.lg]) / (1. + np.exp(-xx))
+            th[self.fx] = self.fixed_value[self.fx]
+        return th
+
+    def finv(self, theta):
+        x = np.asarray(_LOGEXP.finv(np.where(self.kind == 0, theta, 1.0)), dtype=np.float64).copy()
+        if not self.plain:
+            if self.lg.any():
+                t, lo, hi = theta[self.lg], self.lo[self.lg], self.hi[self.lg]
+                x[self.lg] = np.log(np.clip(t - lo, 1e-10, np.inf) / np.clip(hi - t, 1e-10, np.inf))
+            x[self.fx] = 0.0
+        return x
+
+    def gradfactor(self, theta, g):
+        out = _LOGEXP.gradfactor(np.where(self.kind == 0, theta, 1.0), g)
+        if not self.plain:
+            if self.lg.any():
+                t, lo, hi = theta[self.lg], self.lo[self.lg], self.hi[self.lg]
+                out[self.lg] = g[self.lg] * (t - lo) * (hi - t) / (hi - lo)
+            out[self.fx] = 0.0
+        return out
 
 
 class FitResult(object):
@@ -100,6 +151,10 @@ class FitResult(object):
 
 def _model_priors(kernel, likelihood):
     return [p.prior for p in kernel.flattened_parameters()] + [p.prior for p in likelihood.flattened_parameters()]
+
+
+def _model_transforms(kernel, likelihood):
+    return [p.constraint for p in kernel.flattened_parameters()] + [p.constraint for p in likelihood.flattened_parameters()]
 
 
 def draw_starts(kernels, likelihoods, num_restarts):
@@ -146,7 +201,9 @@ def fit_models(engine, kernels, likelihoods, num_restarts=10, max_iters=1000, ro
     priors = _PriorTable([p for i in range(M) for _ in range(R) for p in _model_priors(kernels[i], likelihoods[i])])
 
     theta = np.concatenate(starts)
-    x0 = _LOGEXP.finv(theta)
+    tf = _TransformTable([t for i in range(M) for _ in range(R) for t in _model_transforms(kernels[i], likelihoods[i])], theta)
+    priors.jac &= tf.kind == 0          # the log-Jacobian term exists for Logexp only (paramz: Logistic has none)
+    x0 = tf.finv(theta)
     opts = [make_optimizer(optimizer, x0[off[j]:off[j + 1]], max_iters=max_iters) for j in range(n_inst)]
     x_all = x0.copy()
     stale = np.zeros_like(theta)            # last successfully computed dLML/dtheta per instance
@@ -163,7 +220,7 @@ def fit_models(engine, kernels, likelihoods, num_restarts=10, max_iters=1000, ro
     it = 0
     while active:
         ids = np.asarray(active, dtype=np.int32)
-        theta = _LOGEXP.f(x_all)
+        theta = tf.f(x_all)
         lml, dlml, status, _tries = engine.lml_grad(batch, theta, ids=ids, with_grad=True)
         lp, dlp = priors.log_prior_terms(theta)
         lp_sum = np.add.reduceat(lp, seg_start)
@@ -173,7 +230,7 @@ def fit_models(engine, kernels, likelihoods, num_restarts=10, max_iters=1000, ro
             mask = _segment_mask(off, good, theta.size)
             stale[mask] = dlml[mask]
         g_theta = -(stale + dlp)
-        g_x = _LOGEXP.gradfactor(theta, g_theta)
+        g_x = tf.gradfactor(theta, g_theta)
         nxt_active = []
         for j, is_ok in zip(active, ok):
             a, b = off[j], off[j + 1]
@@ -219,7 +276,10 @@ def fit_models(engine, kernels, likelihoods, num_restarts=10, max_iters=1000, ro
             if best is None or run['f_opt'] < best['f_opt']:
                 best = run
         if best is not None:
-            th = _LOGEXP.f(best['x_opt'])
+            j0 = int(np.nonzero(owner == i)[0][0])
+            x_full = x_all.copy()
+            x_full[off[j0]:off[j0 + 1]] = best['x_opt']                # through instance j0's slice of the transform table
+            th = tf.f(x_full)[off[j0]:off[j0 + 1]]                    # (all restarts of a model share their constraints)
             res.f_opt = best['f_opt']
         else:                                                   # every restart failed: keep the initial parameters
             j0 = int(np.nonzero(owner == i)[0][0])
@@ -289,8 +349,11 @@ def _randomized(kernel, likelihood):
     parameter first (one draw of size P+1), then one rvs(count) per distinct prior in order of first
     appearance."""
     params = kernel.flattened_parameters() + likelihood.flattened_parameters()
-    x = np.random.normal(size=len(params))
-    vals = np.asarray(_LOGEXP.f(x), dtype=np.float64).copy()
+    free = [i for i, p in enumerate(params) if not p.is_fixed]
+    x = np.random.normal(size=len(free))                  # paramz draws `_size_transformed()` numbers
+    vals = np.array([float(p) for p in params], dtype=np.float64)
+    for i, xi in zip(free, x):
+        vals[i] = float(params[i].constraint.f(xi))
     seen = []
     for p in params:
         if p.prior is not None and not any(p.prior is q for q in seen):
@@ -298,6 +361,9 @@ def _randomized(kernel, likelihood):
     for pr in seen:
         ind = [i for i, p in enumerate(params) if p.prior is pr]
         vals[ind] = pr.rvs(len(ind))
+    for i, p in enumerate(params):
+        if p.is_fixed:
+            vals[i] = float(p)
     return vals
 
 
@@ -309,9 +375,12 @@ def map_objective(engine, kernel, likelihood, xs):
     batch = ProgramBatch([kernel] * n)
     engine.upload_programs(batch)
     priors = _PriorTable(_model_priors(kernel, likelihood) * n)
-    theta = _LOGEXP.f(xs.reshape(-1))
+    cur = np.concatenate([kernel.param_array, likelihood.param_array])
+    tf = _TransformTable(_model_transforms(kernel, likelihood) * n, np.tile(cur, n))
+    priors.jac &= tf.kind == 0
+    theta = tf.f(xs.reshape(-1))
     lml, dlml, status, _ = engine.lml_grad(batch, theta, with_grad=True)
     lp, dlp = priors.log_prior_terms(theta)
     f = -lml[:n] - lp.reshape(n, -1).sum(1)
-    g = _LOGEXP.gradfactor(theta, -(dlml[:theta.size] + dlp)).reshape(n, -1)
+    g = tf.gradfactor(theta, -(dlml[:theta.size] + dlp)).reshape(n, -1)
     return f.copy(), g.copy(), status[:n].copy()

@@ -128,9 +128,11 @@ class RBF(Stationary):
 
 
 @_register('GPy.kern.RBFDistanceBuilderKernelKernel')
-class RBFDistanceBuilderKernelKernel(Stationary):
-    """The BOMS "kernel kernel" (fork class used at src/autoks/core/strategies/bayes_opt_gp_strategy.py:27-28; source
-    in notebooks/exploratory/test custom kernels/kernel-kernel.ipynb#2): a Stationary RBF whose unscaled distance
+class RBFDistanceBuilderKernelKernel(RBF):
+    """The BOMS "kernel kernel" (fork class used at src/autoks/core/strategies/bayes_opt_gp_strategy.py:27-28; prototype
+    in notebooks/exploratory/test custom kernels/kernel-kernel.ipynb#2).  A subclass of RBF: the reference wraps it in a
+    `Covariance`, whose tokeniser only knows the classes of KERNEL_DICT (backend/kernel.py:141-150), so the fork class
+    must be one of them -- it prints as SE_1.  An RBF whose unscaled distance
     between two inputs -- model INDICES -- is looked up in the distance builder's matrix,
         k(i, j) = variance * exp(-1/2 (D[i, j] / lengthscale)^2),   D = distance_builder.get_kernel(n_models).
     On the device this is the OP_LOOKUP leaf; the table is uploaded whenever a program batch holding the leaf is."""

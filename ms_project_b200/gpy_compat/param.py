@@ -9,7 +9,7 @@ import copy as _copy
 
 import numpy as np
 
-from .transformations import Logexp
+from .transformations import Logexp, Logistic, Fixed
 
 
 class Param(object):
@@ -58,6 +58,26 @@ class Param(object):
 
     def constrain_positive(self, warning=True):
         self.constraint = Logexp()
+
+    def constrain_bounded(self, lower, upper, warning=True):
+        self.constraint = Logistic(lower, upper)
+        self._v[:] = np.clip(self._v, lower, upper)
+
+    def constrain_fixed(self, value=None, warning=True):
+        if value is not None:
+            self._v[:] = value
+        self.constraint = Fixed()
+
+    fix = constrain_fixed
+
+    def unconstrain_fixed(self):
+        self.constraint = Logexp()
+
+    unfix = unconstrain_fixed
+
+    @property
+    def is_fixed(self):
+        return isinstance(self.constraint, Fixed)
 
     def parameter_names(self):
         return [self.name]
@@ -199,7 +219,30 @@ class Parameterized(object):
         return c
 
     def _size_transformed(self):
-        return self.size          # nothing on the path is fixed or tied
+        """Number of optimisation variables: fixed parameters do not count (BIC's k, backend/model.py:101-104)."""
+        return sum(1 for p in self.flattened_parameters() if not p.is_fixed)
+
+    def constrain_bounded(self, lower, upper, warning=True):
+        for p in self.flattened_parameters():
+            p.constrain_bounded(lower, upper, warning=warning)
+
+    def constrain_fixed(self, value=None, warning=True):
+        for p in self.flattened_parameters():
+            p.constrain_fixed(value, warning=warning)
+
+    def constrain_positive(self, warning=True):
+        """paramz `constrain_positive` on a whole object (KernelKernelGPModel calls it on the likelihood,
+        src/autoks/gp_regression_models.py:100): every parameter gets the Logexp transform."""
+        for p in self.flattened_parameters():
+            p.constrain_positive(warning=warning)
+
+    def set_prior(self, prior, warning=True):
+        for p in self.flattened_parameters():
+            p.set_prior(prior, warning=warning)
+
+    def unset_priors(self):
+        for p in self.flattened_parameters():
+            p.unset_priors()
 
     def randomize(self, rand_gen=None, *args, **kwargs):
         """Priorizable.randomize as paramz/GPy run it: N(0,1) in optimiser space, then prior draws where a
@@ -207,9 +250,15 @@ class Parameterized(object):
         if rand_gen is None:
             rand_gen = np.random.normal
         ps = self.flattened_parameters()
-        x = rand_gen(size=len(ps), *args, **kwargs)
-        vals = np.array([float(p.constraint.f(xi)) for p, xi in zip(ps, x)])
+        free = [p for p in ps if not p.is_fixed]
+        x = rand_gen(size=len(free), *args, **kwargs)          # paramz draws `_size_transformed()` numbers
+        vals = np.array([float(p) for p in ps])
+        xi = iter(x)
+        for i, p in enumerate(ps):
+            if not p.is_fixed:
+                vals[i] = float(p.constraint.f(next(xi)))
         for prior, ind in self.priors.items():
             vals[ind] = prior.rvs(ind.size)
         for p, v in zip(ps, vals):
-            p._v[0] = v
+            if not p.is_fixed:
+                p._v[0] = v

@@ -41,3 +41,38 @@ class Logexp(Transformation):
 
     def __str__(self):
         return '+ve'
+
+
+class Logistic(Transformation):
+    """paramz `Logistic(lower, upper)`: f(x) = lower + (upper - lower) / (1 + exp(-x)) -- what `constrain_bounded` installs
+    (KernelKernelGPModel bounds the surrogate's noise to [1e-9, 1e6] when it has no hyperpriors,
+    src/autoks/gp_regression_models.py:102).  Like in paramz it has no log-Jacobian, so it cannot carry a prior."""
+    domain = 'bounded'
+
+    def __init__(self, lower, upper):
+        assert lower < upper
+        self.lower, self.upper = float(lower), float(upper)
+        self.difference = self.upper - self.lower
+
+    def f(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        return self.lower + self.difference / (1. + np.exp(-np.clip(x, -_log_lim_val, _log_lim_val)))
+
+    def finv(self, f):
+        f = np.asarray(f, dtype=np.float64)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            return np.log(np.clip(f - self.lower, 1e-10, np.inf) / np.clip(self.upper - f, 1e-10, np.inf))
+
+    def gradfactor(self, f, df):
+        return df * (f - self.lower) * (self.upper - f) / self.difference
+
+    def __str__(self):
+        return '{},{}'.format(self.lower, self.upper)
+
+
+class Fixed(Transformation):
+    """Marker for `constrain_fixed`: the parameter keeps its value and is not an optimisation variable."""
+    domain = 'fixed'
+
+    def __str__(self):
+        return 'fixed'

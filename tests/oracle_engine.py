@@ -44,6 +44,10 @@ class OracleEngine(object):
         batch._o_status = np.zeros(n, dtype=np.int32)
         batch._o_tries = np.zeros(n, dtype=np.int32)
         batch._o_expr = [to_oracle_expr(k) for k in batch.kernels]
+        if getattr(batch, 'lookup', None) is not None:      # OP_LOOKUP leaves: the builder's distance table (engine.upload_programs)
+            from oracle import kernels as ok
+            builder, n_models = batch.lookup
+            ok.set_lookup_table(np.asarray(builder.get_kernel(n_models), dtype=np.float64).copy())
         batch.engine = self
         return batch
 

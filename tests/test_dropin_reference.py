@@ -61,6 +61,10 @@ SELECTORS = {
     'uniform_random': lambda ms: ms.UniformRandomModelSelector(base_kernel_names=['SE', 'RQ'], n_restarts_optimizer=2),
     'evolutionary': lambda ms: ms.EvolutionaryModelSelector(base_kernel_names=['SE', 'RQ', 'LIN'], n_restarts_optimizer=2,
                                                             pop_size=8),
+    # BOMS as the reference wires it: CorrelationDistanceBuilder (the reference's own, kern.K served by the product),
+    # BayesOptGPStrategy, KernelKernelGPModel over RBFDistanceBuilderKernelKernel (the OP_LOOKUP leaf), expected improvement
+    # and the inner BoemsSurrogateSelector search (smbo_model_selector.py:43-109)
+    'smbo': lambda ms: ms.SMBOModelSelector(base_kernel_names=['SE', 'RQ'], eval_budget_low_level=8),
 }
 
 
@@ -68,8 +72,9 @@ SELECTORS = {
 def test_reference_selector_runs_unchanged_and_batch_seam_is_equivalent(ref, name):
     make = lambda: SELECTORS[name](ref)       # noqa: E731
     budget = 6
-    sel_a, got_a, log_a = _run(make, batched=False, budget=budget)
-    sel_b, got_b, log_b = _run(make, batched=True, budget=budget)
+    data = _data(24, 2, seed=1) if name == 'smbo' else None
+    sel_a, got_a, log_a = _run(make, batched=False, budget=budget, data=data)
+    sel_b, got_b, log_b = _run(make, batched=True, budget=budget, data=data)
     assert sel_a.n_evals == sel_b.n_evals == budget
     assert len(got_a) >= 1 and all(np.isfinite(s) for _, s in got_a)
     # same candidates, same scores TO THE BIT, same order: the batch seam replays the sequential loop exactly
@@ -77,6 +82,8 @@ def test_reference_selector_runs_unchanged_and_batch_seam_is_equivalent(ref, nam
     assert str(sel_a.best_model()) == str(sel_b.best_model())
     assert sel_a.visited == sel_b.visited
     assert log_a == log_b                      # every callback fires the same number of times in the same order
+    if name == 'smbo':          # SMBOModelSelector holds live strategy / builder objects: no to_dict round trip in the reference either
+        return
     # serialisation round trip of the selector and of its models (base.py:409-443, gp_model.py:98-125)
     sel_c = type(sel_a).from_dict(sel_a.to_dict())
     assert [str(m) for m in sel_c.selected_models] == [str(m) for m in sel_a.selected_models]

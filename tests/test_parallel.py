@@ -101,7 +101,7 @@ def _failing_engine():
     from oracle_engine import OracleEngine
     from ms_project_b200 import program
 
-    class Eng(OracleEngine):
+    class Eng(OracleEngine):          # a fresh class per call, so `tripped` starts False for every fit
         tripped = False
 
         def lml_grad(self, batch, theta, ids=None, with_grad=True):
@@ -122,33 +122,31 @@ def _fit_state(models):
     return np.array([r + [0.0] * (width - len(r)) for r in rec])
 
 
-def _fit_worker(rank, world_size, port, out_dir, policy='lpt'):
+def _fit_worker(rank, world_size, port, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import torch.distributed as dist
     from ms_project_b200 import fitness, parallel
     dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world_size)
     try:
-        models, x, y, md = _fit_problem()
-        np.random.seed(7)
-        parallel.score_models_sharded(models, x, y, fitness.negative_bic, n_restarts=2, engine=_failing_engine(), model_dict=md,
-                                      policy=policy)
-        np.save(os.path.join(out_dir, 'fit%d.npy' % rank), _fit_state(models))
-        np.save(os.path.join(out_dir, 'rng%d.npy' % rank), np.random.get_state()[1])
+        for policy in ('lpt', 'contiguous'):
+            models, x, y, md = _fit_problem()
+            np.random.seed(7)
+            parallel.score_models_sharded(models, x, y, fitness.negative_bic, n_restarts=2, engine=_failing_engine(), model_dict=md,
+                                          policy=policy)
+            np.save(os.path.join(out_dir, 'fit_%s%d.npy' % (policy, rank)), _fit_state(models))
+            np.save(os.path.join(out_dir, 'rng_%s%d.npy' % (policy, rank)), np.random.get_state()[1])
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize('policy', ['lpt', 'contiguous'])
-def test_sharded_fit_with_retry_matches_single_process(tmp_path, policy):
-    """Two ranks, real score_models: identical model state AND identical np.random state on both ranks after a retry on
-    one of them, and both equal to the single-process run (retry draws used to diverge the ranks' streams)."""
+def test_sharded_fit_with_retry_matches_single_process(tmp_path):
+    """Two ranks, real score_models, both shard policies: identical model state AND identical np.random state on both ranks
+    after a retry on one of them, and both equal to the single-process run (retry draws used to diverge the ranks'
+    streams)."""
     import torch.multiprocessing as mp
-    mp.spawn(_fit_worker, args=(2, _free_port(), str(tmp_path), policy), nprocs=2, join=True)
-    f0, f1 = np.load(tmp_path / 'fit0.npy'), np.load(tmp_path / 'fit1.npy')
-    assert np.array_equal(f0, f1, equal_nan=True)
-    assert np.array_equal(np.load(tmp_path / 'rng0.npy'), np.load(tmp_path / 'rng1.npy'))
+    mp.spawn(_fit_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from ms_project_b200 import fitness
     from ms_project_b200.gp_model import score_models
@@ -156,11 +154,16 @@ def test_sharded_fit_with_retry_matches_single_process(tmp_path, policy):
     np.random.seed(7)
     score_models(models, x, y, fitness.negative_bic, n_restarts=2, engine=_failing_engine(), model_dict=md, overlap=False)
     single = _fit_state(models)
-    assert np.array_equal(single[:, :2], f0[:, :2], equal_nan=True)            # scores and failed flags: same bits
-    assert np.array_equal(single[:, 3:], f0[:, 3:])                            # optimised parameters: same bits
-    assert np.array_equal(np.random.get_state()[1], np.load(tmp_path / 'rng0.npy'))
-    i = FIT_NAMES.index(FAIL_ONCE)
-    assert np.isfinite(f0[i, 0]) and f0[i, 1] == 0.0                           # the retry recovered the model
-    assert f0[i, 2] > 0
-    # the second occurrence of the shared kernel object started from the first one's optimum: fewer evaluations, same fit
-    assert f0[-1, 2] < f0[0, 2] and abs(f0[-1, 0] - f0[0, 0]) < 1e-3 * abs(f0[0, 0])
+    rng_single = np.random.get_state()[1]
+    for policy in ('lpt', 'contiguous'):
+        f0, f1 = np.load(tmp_path / ('fit_%s0.npy' % policy)), np.load(tmp_path / ('fit_%s1.npy' % policy))
+        assert np.array_equal(f0, f1, equal_nan=True)
+        assert np.array_equal(np.load(tmp_path / ('rng_%s0.npy' % policy)), np.load(tmp_path / ('rng_%s1.npy' % policy)))
+        assert np.array_equal(single[:, :2], f0[:, :2], equal_nan=True)            # scores and failed flags: same bits
+        assert np.array_equal(single[:, 3:], f0[:, 3:])                            # optimised parameters: same bits
+        assert np.array_equal(rng_single, np.load(tmp_path / ('rng_%s0.npy' % policy)))
+        i = FIT_NAMES.index(FAIL_ONCE)
+        assert np.isfinite(f0[i, 0]) and f0[i, 1] == 0.0                           # the retry recovered the model
+        assert f0[i, 2] > 0
+        # the second occurrence of the shared kernel object started from the first one's optimum: fewer evaluations, same fit
+        assert f0[-1, 2] < f0[0, 2] and abs(f0[-1, 0] - f0[0, 0]) < 1e-3 * abs(f0[0, 0])

@@ -91,7 +91,8 @@ def launches(tag):
     out.append('| **all** | %d | %.2f | 100%% |' % (sum(a[0] for a in agg.values()), total / 1e6))
     dm = sum(ns for k, (n, ns) in agg.items() if k in ('chol_update_kernel', 'inv_update_kernel', 'kinv_kernel',
                                                      'chol_update64_kernel', 'inv_update64_kernel', 'kinv64_kernel',
-                                                     'chol_trsm_kernel', 'inv_trsm_kernel', 'gemm_kernel'))
+                                                     'chol_update64_tma_kernel', 'inv_update64_tma_kernel', 'kinv64_tma_kernel',
+                                                     'trsm64_kernel', 'chol_trsm_kernel', 'inv_trsm_kernel', 'gemm_kernel'))
     out += ['', 'DMMA tile-GEMM kernels together: %.1f%% of the kernel time.' % (100 * dm / total)]
     shutil.copy(path, os.path.join(PROF, 'launches_%s.csv' % tag))
     return '\n'.join(out) + '\n'
@@ -104,8 +105,12 @@ def main():
     if txt:
         open(os.path.join(PROF, 'launches_%s.md' % tag), 'w').write(txt)
     out = ['# ncu `--set full --clock-control none` captures (%s)' % tag, '',
-           'Command: `python tools/perf_probe.py 2048 32 1` (32 C2 kernels, N = 2048, one NLML+grad evaluation), one launch of '
-           'each kernel; script `tools/ncu_r01.sh`.  Reports themselves stay in `gpurun_out/` (scratch, MBs each).', '']
+           'Commands: `python tools/perf_probe.py 2048 32 1` (32 C2 kernels, N = 2048, one NLML+grad evaluation) for the scoring '
+           'kernels, `python tools/perf_c5.py 16384` for `c5upd` (the first K = 512 trailing update of the N = 16384 Cholesky), '
+           '`python tools/bench_configs.py --configs c3` for the Hellinger kernels; one launch of each kernel; script '
+           '`tools/ncu_r02.sh`.  Reports themselves stay in `gpurun_out/` (scratch, MBs each).', '']
+    traffic = {'source': 'ncu --set full --clock-control none, python tools/perf_probe.py 2048 32 1 (32 items per launch), tag %s; '
+                         'see profiles/ncu_%s.md' % (tag, tag), 'items_per_launch': 32}
     for rep in sorted(glob.glob(os.path.join(OUT, 'prof_*_%s.ncu-rep' % tag))):
         d = raw_page(rep)
         name = os.path.basename(rep)[5:-len('_%s.ncu-rep' % tag)]
@@ -129,6 +134,12 @@ def main():
             except Exception:
                 return None
         t = num('gpu__time_duration.sum')
+        if name in ('kinv', 'grad', 'build') and t:
+            pipe = d.get('sm__ops_path_tensor_src_fp64.avg.pct_of_peak_sustained_elapsed' if name == 'kinv'
+                         else 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', ('nan', ''))[0]
+            traffic[{'kinv': 'kinv64_kernel', 'grad': 'poly_grad_kernel', 'build': 'poly_build_kernel'}[name]] = {
+                'dram_bytes_read': num('dram__bytes_read.sum'), 'dram_bytes_write': num('dram__bytes_write.sum'),
+                'duration_ms': t * 1e3, 'pipe_pct': float(pipe.replace(',', '')) if pipe not in ('', 'nan') else None}
         dfma, dmul, dadd = (num('smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed'),
                             num('smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed'),
                             num('smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed'))
@@ -154,6 +165,9 @@ def main():
                            % ((rd + wr) / t / 1e9, 100 * (rd + wr) / t / 6544e9))
         out.append('')
     open(os.path.join(PROF, 'ncu_%s.md' % tag), 'w').write('\n'.join(out) + '\n')
+    if 'kinv64_kernel' in traffic:
+        import json
+        json.dump(traffic, open(os.path.join(PROF, 'ncu_traffic_%s.json' % tag), 'w'), indent=1)
     print('\n'.join(out[:80]))
     if txt:
         print(txt)
