@@ -335,11 +335,15 @@ void launch_hellinger_pairs(const double* logdet, const double* G, int S, int n,
 #define HP_LAUNCH(R, MINB, COLS) hellinger_pair_kernel<R, MINB, COLS><<<grid, TS_THREADS, 0, st>>>(logdet, G, S, n, pair_i, pair_j, tol, h, hstatus)
   // measured on C3 (124 750 pairs x 20 samples, n = 100): one column per barrier with three CTAs per SM 0.224 s, two columns
   // per barrier with three CTAs (80 B of spills) 0.245 s, with two CTAs (no spills) 0.273 s; round 1's kernel 0.369 s.
+  // Letting the pivot's owner compute the reciprocal before the barrier (one thread instead of 256 redundant ones, 12 % fewer
+  // instructions) is SLOWER, 0.25-0.29 s: the 60-cycle reciprocal then sits in front of the barrier for all eight warps.
   // A DMMA formulation (trailing matrix in 8 x 8 accumulator tiles over 4 or 8 warps, 13 panel steps: one-warp shuffle Cholesky
   // of the 8 x 8 diagonal block, thread-per-row panel solve, two DMMAs per tile update) was correct but no faster: 0.218-0.279 s
   // -- 47 % of its stall samples sit behind the three barriers of a panel step, whose serial phases leave 7 of 8 warps idle
   // (profiles/experiments/); removed again.
   if (n <= 64) HP_LAUNCH(4, 4, 2);
+  else if (n <= 80) HP_LAUNCH(5, 4, 1);
+  else if (n <= 96) HP_LAUNCH(6, 3, 1);
   else if (n <= 112) HP_LAUNCH(7, 3, 1);
   else HP_LAUNCH(8, 2, 2);
 #undef HP_LAUNCH
