@@ -211,13 +211,24 @@ def score_models(models, x, y, scoring_func, optimizer=None, n_restarts=10, engi
     return [m.score for m in models]
 
 
+# L-BFGS-B evaluations a leaf of each family adds to a 3-restart fit, relative to SE: least squares over the per-model counts of
+# the C2 fit (256 candidates, profiles/fit_evals_r02.json: 89 / 132 / 314 / 108 evaluations per SE / RQ / PER / LIN leaf,
+# R^2 = 0.52 -- periodic surfaces need about three times the iterations; the rest of the 50x spread is not predictable from the
+# kernel's shape)
+_EVALS_PER_LEAF = {'SE': 1.0, 'RQ': 1.5, 'PER': 3.5, 'LIN': 1.2}
+
+
 def model_cost(kernel, n_data):
-    """Relative cost of fitting one model, for balancing shards: per evaluation N^3 for the factorisation + inverse plus the
-    element-wise passes that scale with the number of leaves, times the number of evaluations an L-BFGS-B
-    run needs, which grows with the number of parameters."""
-    n_params = kernel.size + 1
-    n_leaves = sum(1 for _ in kernel.flattened_parameters()) / 2.5 + 1.0
-    return (float(n_data) ** 3 + 150.0 * n_leaves * float(n_data) ** 2) * (10.0 + 4.0 * n_params)
+    """Relative cost of fitting one model, for balancing shards: (cost of one evaluation: N^3 for the factorisation + inverse
+    plus the element-wise passes, which scale with the number of leaves) x (expected number of evaluations,
+    which grows with the leaves and their families).  With this cost LPT leaves the busiest of 8 ranks 10 % above the mean on
+    C2 (17 % with a parameter-count cost, 19 % with equal costs, 0.1 % if the counts were known in advance)."""
+    leaves = []
+    kernel.traverse(lambda q: leaves.append(getattr(q, 'op_name', None)) if getattr(q, 'op_name', None) is not None
+                    and not hasattr(q, 'parts') or (getattr(q, 'op_name', None) is not None and q.parts == [q]) else None)
+    leaves = [f for f in leaves if f is not None] or ['SE']
+    n_evals = 0.5 + sum(_EVALS_PER_LEAF.get(f, 1.0) for f in leaves)
+    return (float(n_data) ** 3 + 150.0 * len(leaves) * float(n_data) ** 2) * n_evals
 
 
 def _prepare(m, model_dict):
