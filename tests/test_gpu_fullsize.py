@@ -48,6 +48,17 @@ def test_c2_size_parity_and_schedule_independence(engine):
         engine.set_tile64(True)
     assert (st_w == 0).all() and np.array_equal(lml_w, lml80) and np.array_equal(g_w, g80)
     assert lml_w1[33] == lml80[33] and np.array_equal(g_w1[a:b], g80[a:b])
+    # operand staging of the 64 x 64 tile GEMMs: TMA + mbarrier ring (default, three swizzle modes, 3- and 4-stage rings) and
+    # cp.async + block barrier give the same bits (tile_gemm64_tma.cuh: every element sums its products in ascending k)
+    try:
+        for mode in (0, 1, 2, 4):
+            engine.set_tma(mode)
+            lml_t, g_t, st_t, _ = [a_.copy() for a_ in engine.lml_grad(batch, theta)]
+            assert (st_t == 0).all() and np.array_equal(lml_t, lml80) and np.array_equal(g_t, g80), mode
+            lml_t1, g_t1, _, _ = [a_.copy() for a_ in engine.lml_grad(batch, theta, ids=np.array([33], dtype=np.int32))]
+            assert lml_t1[33] == lml80[33] and np.array_equal(g_t1[a:b], g80[a:b]), mode
+    finally:
+        engine.set_tma(3)
 
 
 def test_c5_size_cholesky_and_gradient_properties(engine):
