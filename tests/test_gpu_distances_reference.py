@@ -5,9 +5,9 @@ FrobeniusDistanceBuilder, CorrelationDistanceBuilder, unmodified, run through te
 kernels with the BOMS hyperpriors over 40 points: prior sampling (distance/util.py), `chol_safe` log-determinants, the
 asymmetric skip rule of `hellinger_distance`, the averaging and the float32 vectors of the other two are the reference's code
 (only `kern.K` comes from the oracle).  The device builders get the same kernels and the same probability samples.
-Tolerances: log-determinants 1e-9, Hellinger distances 1e-7 (squared), Frobenius 1e-5 relative, correlation 1e-4 absolute
+Tolerances: log-determinants 1e-9, Hellinger distances 1e-7 (squared), Frobenius 1e-5 relative, correlation 5e-4 absolute
 (the reference accumulates float32 vectors in float32; measured on B200: Hellinger / Frobenius agree to the stated bounds,
-the correlation distances to 4.5e-5 = the reference's own d(i, i))."""
+the correlation distances to 1.5e-4; the reference's own d(i, i) is 4.5e-5)."""
 import json
 import os
 
@@ -66,6 +66,8 @@ def test_device_builders_match_the_reference_builders(engine, name):
     elif name == 'frobenius':
         assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-5, float(np.max(np.abs(got - ref)))
     else:
-        # sqrt(1/2 (1 - corr)) amplifies the reference's float32 rounding near corr = 1: its own d(i, i) is 4.5e-5, not 0
-        assert np.max(np.abs(got - ref)) <= 1e-4, float(np.max(np.abs(got - ref)))
+        # sqrt(1/2 (1 - corr)) amplifies the reference's float32 rounding (vectors AND accumulations are float32) near
+        # corr = 1: its own d(i, i) is 4.5e-5 instead of 0, its small distances are off by up to 1.5e-4; the device values are
+        # checked against the float64 evaluation to 1e-9 in tests/test_gpu_vector_distances.py
+        assert np.max(np.abs(got - ref)) <= 5e-4, float(np.max(np.abs(got - ref)))
         assert np.max(np.abs(np.diag(got))) <= 1e-7 and np.max(np.abs(np.diag(ref))) <= 1e-4
