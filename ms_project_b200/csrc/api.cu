@@ -145,7 +145,7 @@ Layout carve(void* ws, int N, int D, int slots, int max_params) {
 
 extern "C" {
 
-const char* b200gp_version(void) { return "b200gp 0.1 (sm_100a, FP64 DMMA)"; }
+const char* b200gp_version(void) { return "b200gp 0.2 (sm_100a, FP64 DMMA, TMA-fed tile GEMMs)"; }
 
 int b200gp_create(int device, void* cuda_stream, b200gp_ctx** out) {
   if (!out) return -1;

@@ -224,9 +224,13 @@ def model_cost(kernel, n_data):
     which grows with the leaves and their families).  With this cost LPT leaves the busiest of 8 ranks 10 % above the mean on
     C2 (17 % with a parameter-count cost, 19 % with equal costs, 0.1 % if the counts were known in advance)."""
     leaves = []
-    kernel.traverse(lambda q: leaves.append(getattr(q, 'op_name', None)) if getattr(q, 'op_name', None) is not None
-                    and not hasattr(q, 'parts') or (getattr(q, 'op_name', None) is not None and q.parts == [q]) else None)
-    leaves = [f for f in leaves if f is not None] or ['SE']
+
+    def visit(q):                      # leaf kernels carry a device opcode family; sums, products and parameters do not
+        family = getattr(q, 'op_name', None)
+        if family is not None:
+            leaves.append(family)
+    kernel.traverse(visit)
+    leaves = leaves or ['SE']
     n_evals = 0.5 + sum(_EVALS_PER_LEAF.get(f, 1.0) for f in leaves)
     return (float(n_data) ** 3 + 150.0 * len(leaves) * float(n_data) ** 2) * n_evals
 
