@@ -542,13 +542,15 @@ def run_ours(args, rank, world, local_rank):
             # the CPU baselines on this box's host cores, on a stratified sample of the SAME item list:
             # B = process pool, one candidate per core, BLAS threads 1 (the strongest); A = sequential, all BLAS threads per item
             pool = CpuPool(X, y, items, thetas, noises)
-            idx = sample_indices(n_items, 3 * pool.cores)
+            idx = sample_indices(n_items, 5 * pool.cores)
             pool.rate(idx[:pool.cores])                    # warm the workers
-            rate_b, done_b, failed_b, dt_b = pool.rate(idx[pool.cores:])
+            rounds = [pool.rate(idx[(1 + 2 * r) * pool.cores:(3 + 2 * r) * pool.cores]) for r in range(2)]
             pool.close()
+            rate_b, done_b, failed_b, dt_b = max(rounds, key=lambda t: t[0])       # the FASTER of two rounds: a baseline errs high
             line['cpu_baseline'] = {'value': rate_b, 'unit': UNIT, 'cores': pool.cores, 'kind': 'port',
-                                    'sample': 'process pool, one candidate per core, BLAS threads = 1: %d evenly spaced items of the 768, '
-                                              '%.1f s, %d not PD (NumPy/SciPy-LAPACK oracle)' % (done_b, dt_b, failed_b)}
+                                    'sample': 'process pool, one candidate per core, BLAS threads = 1: the faster of two rounds of %d '
+                                              'evenly spaced items of the 768 (%.1f s, %d not PD; the other round %.2f kernels/s); '
+                                              'NumPy/SciPy-LAPACK oracle' % (done_b, dt_b, failed_b, min(r[0] for r in rounds))}
             rate_a, cores_a, done_a, failed_a, dt_a = cpu_reference_rate(X, y, items, thetas, noises, 12.0, sample_indices(n_items, 16))
             line['cpu_baseline_sequential'] = {'value': rate_a, 'unit': UNIT, 'cores': cores_a, 'kind': 'port',
                                                'sample': 'sequential over %d evenly spaced items, all BLAS threads per item, %.1f s, %d not PD'
