@@ -131,6 +131,53 @@ hellinger_pair_kernel(const double* __restrict__ logdet, const double* __restric
   }
 }
 
+// The same work item on the 16 x 8 thread grid of rect_potrf_pivots (128 threads per matrix).
+template <int RP, int MINB>
+__global__ void __launch_bounds__(TR_THREADS, MINB)
+hellinger_pair_rect_kernel(const double* __restrict__ logdet, const double* __restrict__ G, int S, int n,
+                           const int* __restrict__ pair_i, const int* __restrict__ pair_j, double tol,
+                           double* __restrict__ h, int* __restrict__ hstatus) {
+  __shared__ RectPotrfSmem<RP> T;
+  const int pr = blockIdx.x, s = blockIdx.y;
+  const int mi = pair_i[pr], mj = pair_j[pr];
+  const double ldi = logdet[(size_t)mi * S + s], ldj = logdet[(size_t)mj * S + s];
+  double ldpq = ldi;
+  int bad = 0;
+  if (fabs(ldi - ldj) > tol) {        // uniform across the CTA
+    const double* Gi = G + ((size_t)mi * S + s) * n * n;
+    const double* Gj = G + ((size_t)mj * S + s) * n * n;
+    const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
+    double a[RP * (RP + 1)];
+#pragma unroll
+    for (int p = 0; p < RP; p++)
+#pragma unroll
+      for (int q = 0; q <= 2 * p + 1; q++) {
+        const int i = ty + 16 * p, c = tx + 8 * q;
+        double v = (i == c) ? 1.0 : 0.0;
+        if (i < n && c <= i) v = 0.5 * (__ldg(Gi + (size_t)i * n + c) + __ldg(Gj + (size_t)i * n + c));
+        a[tr_idx(p, q)] = v;
+      }
+    rect_potrf_pivots<RP>(a, T, n);
+    double sum = 0.0;                 // warp 0 sums log(piv[0..n)) in a fixed order
+    if (threadIdx.x < 32) {
+#pragma unroll
+      for (int r = 0; r < (16 * RP + 31) / 32; r++) {
+        const int j = threadIdx.x + 32 * r;
+        if (j < n) sum += log(T.piv[j]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    ldpq = sum;
+    bad = T.fail != 0;
+  }
+  if (threadIdx.x == 0) {
+    const double log_h = 0.25 * (ldi + ldj) - 0.5 * ldpq;
+    h[(size_t)pr * S + s] = bad ? nan("") : 1.0 - exp(log_h);
+    hstatus[(size_t)pr * S + s] = bad;
+  }
+}
+
 __global__ void hellinger_reduce_kernel(const double* __restrict__ h, const int* __restrict__ hstatus, int S, int npairs,
                                         double* __restrict__ dist, int* __restrict__ status) {
   const int pr = blockIdx.x * blockDim.x + threadIdx.x;
@@ -333,19 +380,21 @@ void launch_hellinger_pairs(const double* logdet, const double* G, int S, int n,
                             int npairs, double tol, double* h, int* hstatus, double* dist, int* status, cudaStream_t st) {
   dim3 grid(npairs, S);               // x = pair (fastest), y = sample: sample-major execution order, see the kernel
 #define HP_LAUNCH(R, MINB, COLS) hellinger_pair_kernel<R, MINB, COLS><<<grid, TS_THREADS, 0, st>>>(logdet, G, S, n, pair_i, pair_j, tol, h, hstatus)
-  // measured on C3 (124 750 pairs x 20 samples, n = 100): one column per barrier with three CTAs per SM 0.224 s, two columns
-  // per barrier with three CTAs (80 B of spills) 0.245 s, with two CTAs (no spills) 0.273 s; round 1's kernel 0.369 s.
-  // Letting the pivot's owner compute the reciprocal before the barrier (one thread instead of 256 redundant ones, 12 % fewer
-  // instructions) is SLOWER, 0.25-0.29 s: the 60-cycle reciprocal then sits in front of the barrier for all eight warps.
-  // A DMMA formulation (trailing matrix in 8 x 8 accumulator tiles over 4 or 8 warps, 13 panel steps: one-warp shuffle Cholesky
-  // of the 8 x 8 diagonal block, thread-per-row panel solve, two DMMAs per tile update) was correct but no faster: 0.218-0.279 s
-  // -- 47 % of its stall samples sit behind the three barriers of a panel step, whose serial phases leave 7 of 8 warps idle
-  // (profiles/experiments/); removed again.
-  if (n <= 64) HP_LAUNCH(4, 4, 2);
-  else if (n <= 80) HP_LAUNCH(5, 4, 1);
-  else if (n <= 96) HP_LAUNCH(6, 3, 1);
-  else if (n <= 112) HP_LAUNCH(7, 3, 1);
+#define HR_LAUNCH(RP, MINB) hellinger_pair_rect_kernel<RP, MINB><<<grid, TR_THREADS, 0, st>>>(logdet, G, S, n, pair_i, pair_j, tol, h, hstatus)
+  // Measured on C3 (124 750 pairs x 20 samples, n = 100; round 1's kernel: 0.369 s):
+  //   16 x 16 thread grid (256 threads): one column per barrier, three CTAs per SM 0.224 s; two columns per barrier 0.245 s
+  //     (three CTAs, 80 B of spills) / 0.273 s (two CTAs); pivot reciprocal by its owner in front of the barrier 0.25-0.29 s
+  //   16 x 8 thread grid (128 threads, 167 registers): three CTAs per SM 0.187 s (kept), two CTAs 0.242 s
+  //   DMMA formulation (8 x 8 accumulator tiles over 4 or 8 warps, 13 panel steps): correct, 0.218-0.279 s, 47 % of its
+  //     stall samples behind the three barriers of a panel step; removed (profiles/experiments/)
+  // Occupancy decides every comparison: the kernel is bound by the latency chain of an elimination step (barrier -> pivot
+  // -> reciprocal -> scaled column -> multiply-adds), which only other resident matrices can hide.
+  if (n <= 64) HR_LAUNCH(4, 6);
+  else if (n <= 80) HR_LAUNCH(5, 4);
+  else if (n <= 96) HR_LAUNCH(6, 3);
+  else if (n <= 112) HR_LAUNCH(7, 3);
   else HP_LAUNCH(8, 2, 2);
+#undef HR_LAUNCH
 #undef HP_LAUNCH
   g_launch_count++;
   hellinger_reduce_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(h, hstatus, S, npairs, dist, status);

@@ -105,3 +105,63 @@ __device__ __forceinline__ void small_potrf_pivots(double (&a)[R * (R + 1) / 2],
 }
 
 }  // namespace b200gp
+
+namespace b200gp {
+
+// ------------------------------------------------------------------------------------------------
+// The same factorisation on a 16 x 8 thread grid (128 threads, four warps): thread (ty, tx) owns the elements
+// (ty + 16 p, tx + 8 q), p < RP, q < 2 RP, of which the block-lower part q <= 2 p + 1 is stored -- RP (RP + 1) register
+// blocks, 56 doubles for RP = 7 (n <= 112).  Per elimination step a thread loads RP row operands and 2 RP column operands
+// for up to RP (RP + 1) multiply-adds: twice the arithmetic per operand load, pivot reciprocal and barrier of the 16 x 16
+// grid, i.e. half the instructions per matrix, at the price of four instead of eight warps per matrix.
+// ------------------------------------------------------------------------------------------------
+constexpr int TR_THREADS = 128;
+
+template <int RP>
+struct RectPotrfSmem {
+  double col[2][16 * RP];     // [step parity][row]
+  double piv[16 * RP];
+  int fail;
+};
+
+__host__ __device__ constexpr int tr_idx(int p, int q) { return p * (p + 1) + q; }    // block (p, q), q <= 2 p + 1
+
+template <int RP>
+__device__ __forceinline__ void rect_potrf_pivots(double (&a)[RP * (RP + 1)], RectPotrfSmem<RP>& S, int nact) {
+  const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
+  if (threadIdx.x == 0) S.fail = 0;
+  for (int t = threadIdx.x; t < 16 * RP; t += TR_THREADS) S.piv[t] = 1.0;
+#pragma unroll
+  for (int qb = 0; qb < 2 * RP; qb++) {         // block column of 8 matrix columns
+    const int pb = qb >> 1;                     // first block row with live elements in these columns
+#pragma unroll 1
+    for (int jj = 0; jj < 8; jj++) {
+      const int j = qb * 8 + jj;
+      if (j >= nact) break;                     // uniform
+      double* cA = S.col[j & 1];
+      if (tx == jj) {
+#pragma unroll
+        for (int p = pb; p < RP; p++) cA[ty + 16 * p] = a[tr_idx(p, qb)];
+      }
+      __syncthreads();
+      const double d0 = cA[j];
+      const double i0 = 1.0 / d0;
+      if (threadIdx.x == 0) {
+        S.piv[j] = d0;
+        if ((!(d0 > 0.0) || !(d0 < 1.7e308)) && S.fail == 0) S.fail = j + 1;
+      }
+      double c0[2 * RP];
+#pragma unroll
+      for (int q = qb; q < 2 * RP; q++) c0[q] = cA[tx + 8 * q] * i0;
+#pragma unroll
+      for (int p = pb; p < RP; p++) {
+        const double r0 = cA[ty + 16 * p];
+#pragma unroll
+        for (int q = qb; q <= 2 * p + 1; q++) a[tr_idx(p, q)] = fma(-r0, c0[q], a[tr_idx(p, q)]);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+}  // namespace b200gp

@@ -77,6 +77,25 @@ def test_precompute_and_distances_match_oracle():
     assert abs(d01 ** 2 - D_ref[0, 5] ** 2) < 1e-7
 
 
+@pytest.mark.parametrize('n', [17, 64, 65, 80, 96, 97, 112, 113, 128])
+def test_pair_distances_at_every_subset_size_class(n):
+    """The pair kernel is instantiated per size class (16-row block counts 4 ... 8, two thread grids): every class, at its
+    edges, against the oracle."""
+    rng = np.random.default_rng(n)
+    x = rng.random((n, 3))
+    x = (x - x.mean(0)) / x.std(0)
+    am, builder, prob, noise_prior, pool = _setup(x, 10, 2, ['SE', 'RQ'], 3)
+    infos, _lam = _oracle_infos(pool, x, prob, noise_prior)
+    for m, (ld_ref, _G) in zip(am.models, infos):
+        assert np.allclose(m.info.log_det, ld_ref, rtol=1e-9, atol=1e-8)
+    for i in range(len(pool)):
+        builder.compute_distance(am, [i], list(range(i + 1, len(pool))))
+    D, D_ref = builder.get_kernel(len(pool)), ohell.distance_matrix(infos)
+    off = ~np.eye(len(pool), dtype=bool)
+    assert np.allclose(D[off] ** 2, D_ref[off] ** 2, rtol=0, atol=1e-7), np.max(np.abs(D[off] ** 2 - D_ref[off] ** 2))
+    assert np.all(builder.last_status == 0)
+
+
 def test_metric_axioms_like_reference_tests():
     x = np.array([[1, 2], [4, 5], [6, 7], [8, 9], [10, 11]], dtype=np.float64)     # test_distance.py:19
     am, builder, prob, noise_prior, pool = _setup(x, 50, 2, ['SE', 'RQ'], 2)
