@@ -1,4 +1,5 @@
-// Pivots of the Cholesky factorisation of ONE small SPD matrix (order <= 16 R <= 128) held in REGISTERS by a 256-thread CTA:
+// Pivots of the Cholesky factorisation of ONE small SPD matrix (order <= 16 R <= 128) held in REGISTERS by a 256-thread CTA
+// (16 x 16 thread grid; the 128-thread 16 x 8 grid the pair kernel uses up to order 112 follows at the end of the file):
 // the log-determinant engine of the Hellinger pair kernel (hellinger.cu), where 2.5 million 100 x 100 factorisations make
 // up configuration C3.
 //
