@@ -6,6 +6,7 @@
 //   pairs:       per (pair, sample s)   if |ld_i - ld_j| > tol: logdet(1/2 (G_i,s + G_j,s)) else ld_i
 //                                        h_s = 1 - exp(1/4 (ld_i + ld_j) - 1/2 logdet_pq);  d = sqrt(clip(mean_s h_s, 0, 1))
 // Each small factorisation (n <= 128) is one CTA running the in-register Cholesky of tile_potrf.cuh.
+#include <cstdlib>
 #include "kernels.cuh"
 #include "kprog.cuh"
 #include "tile_potrf.cuh"
@@ -170,6 +171,59 @@ hellinger_pair_rect_kernel(const double* __restrict__ logdet, const double* __re
     }
     ldpq = sum;
     bad = T.fail != 0;
+  }
+  if (threadIdx.x == 0) {
+    const double log_h = 0.25 * (ldi + ldj) - 0.5 * ldpq;
+    h[(size_t)pr * S + s] = bad ? nan("") : 1.0 - exp(log_h);
+    hstatus[(size_t)pr * S + s] = bad;
+  }
+}
+
+// The same work item on the look-ahead factorisation (rect_potrf_pivots_la: next column and its pivot reciprocal published
+// under the trailing update, one reciprocal per step and matrix).
+template <int RP, int MINB>
+__global__ void __launch_bounds__(TR_THREADS, MINB)
+hellinger_pair_la_kernel(const double* __restrict__ logdet, const double* __restrict__ G, int S, int n,
+                         const int* __restrict__ pair_i, const int* __restrict__ pair_j, double tol,
+                         double* __restrict__ h, int* __restrict__ hstatus) {
+  __shared__ RectLaSmem<RP> T;
+  const int pr = blockIdx.x, s = blockIdx.y;
+  const int mi = pair_i[pr], mj = pair_j[pr];
+  const double ldi = logdet[(size_t)mi * S + s], ldj = logdet[(size_t)mj * S + s];
+  double ldpq = ldi;
+  int bad = 0;
+  if (fabs(ldi - ldj) > tol) {        // uniform across the CTA
+    const double* Gi = G + ((size_t)mi * S + s) * n * n;
+    const double* Gj = G + ((size_t)mj * S + s) * n * n;
+    const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
+    double a[RP * (RP + 1)];
+#pragma unroll
+    for (int p = 0; p < RP; p++)
+#pragma unroll
+      for (int q = 0; q <= 2 * p + 1; q++) {
+        const int i = ty + 16 * p, c = tx + 8 * q;
+        double v = (i == c) ? 1.0 : 0.0;
+        if (i < n && c <= i) v = 0.5 * (__ldg(Gi + (size_t)i * n + c) + __ldg(Gj + (size_t)i * n + c));
+        a[tr_idx(p, q)] = v;
+      }
+    rect_potrf_pivots_la<RP>(a, T, n);
+    double sum = 0.0;                 // warp 0 sums log(piv[0..n)) in a fixed order and checks the pivots
+    if (threadIdx.x < 32) {
+      int badp = 0;
+#pragma unroll
+      for (int r = 0; r < (16 * RP + 31) / 32; r++) {
+        const int j = threadIdx.x + 32 * r;
+        if (j < n) {
+          const double pv = T.piv[j];
+          sum += log(pv);
+          badp |= (!(pv > 0.0) || !(pv < 1.7e308)) ? 1 : 0;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      bad = __any_sync(0xffffffffu, badp);
+    }
+    ldpq = sum;
   }
   if (threadIdx.x == 0) {
     const double log_h = 0.25 * (ldi + ldj) - 0.5 * ldpq;
@@ -389,6 +443,15 @@ void launch_hellinger_pairs(const double* logdet, const double* G, int S, int n,
   //     stall samples behind the three barriers of a panel step; removed (profiles/experiments/)
   // Occupancy decides every comparison: the kernel is bound by the latency chain of an elimination step (barrier -> pivot
   // -> reciprocal -> scaled column -> multiply-adds), which only other resident matrices can hide.
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("B200GP_HP_VARIANT"); variant = e ? atoi(e) : 1; }
+#define HL_LAUNCH(RP, MINB) hellinger_pair_la_kernel<RP, MINB><<<grid, TR_THREADS, 0, st>>>(logdet, G, S, n, pair_i, pair_j, tol, h, hstatus)
+  if (variant == 1 && n <= 112) {
+    if (n <= 64) HL_LAUNCH(4, 6);
+    else if (n <= 80) HL_LAUNCH(5, 4);
+    else if (n <= 96) HL_LAUNCH(6, 3);
+    else HL_LAUNCH(7, 3);
+  } else
   if (n <= 64) HR_LAUNCH(4, 6);
   else if (n <= 80) HR_LAUNCH(5, 4);
   else if (n <= 96) HR_LAUNCH(6, 3);

@@ -165,4 +165,128 @@ __device__ __forceinline__ void rect_potrf_pivots(double (&a)[RP * (RP + 1)], Re
   __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Look-ahead form of the 16 x 8 factorisation (the one the pair kernel runs).  Per elimination step j the chain
+// barrier -> pivot -> reciprocal -> scaled operands -> multiply-adds -> publish column j + 1 -> barrier is what bounds the
+// kernel (ncu: FP64 pipe 37 % busy, issue slots 44 %), so everything that can leave it does:
+//   * the block column that holds column j + 1 is updated FIRST, and its owners publish column j + 1 (into the other
+//     buffer) before the rest of the trailing update is issued: by the time the last multiply-add of step j retires the
+//     next column has long been visible, and the barrier costs its own latency only;
+//   * the owner of pivot j + 1 computes the reciprocal right after that first update -- its MUFU + Newton chain runs under
+//     the remaining multiply-adds -- and publishes it with the column, so after the barrier a thread loads 1 / d_j instead
+//     of computing it (one reciprocal per step and matrix instead of one per thread);
+//   * the ROW operands carry the 1 / d_j factor (RP multiplies per step instead of 2 RP on the column operands);
+//   * the last step of a block column skips that block column (its eight columns are all eliminated).
+// Same arithmetic up to the rounding of the reciprocal (MUFU.RCP64H + two Newton steps, ~1 ulp, instead of the IEEE divide).
+// ------------------------------------------------------------------------------------------------
+template <int RP>
+struct RectLaSmem {
+  double col[2][16 * RP];     // [step parity][row]: column j as it stands when step j starts
+  double inv[2];              // [step parity]: 1 / d_j
+  double scratch[16 * RP + 8]; // where the threads that do not own the next column store (never read; offset by half the banks)
+  double piv[16 * RP];        // pivots d_j (1 on the padding)
+};
+
+__device__ __forceinline__ double rcp_newton(double m) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(m));     // MUFU.RCP64H
+  double e = fma(-m, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-m, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// One elimination step: column j = 8 QB + jj, PAR = j & 1 (a template argument, so every shared-memory address of the step
+// is a per-thread base plus an immediate), LAST = (jj == 7).
+template <int RP, int QB, bool LAST, int PAR>
+__device__ __forceinline__ void rect_la_step(double (&a)[RP * (RP + 1)], RectLaSmem<RP>& S, int jj, int ty, int tx) {
+  constexpr int PB = QB >> 1;
+  constexpr int QN = LAST ? QB + 1 : QB;         // block column of column j + 1
+  constexpr int PN = QN >> 1;
+  constexpr int QF = LAST ? QB + 2 : QB + 1;     // first block column of the remaining update
+  const double* cA = S.col[PAR];
+  __syncthreads();
+  const double i0 = S.inv[PAR];
+  double r0[RP];
+#pragma unroll
+  for (int p = PB; p < RP; p++) r0[p] = cA[ty + 16 * p] * i0;
+  // the first LA_PRE operands of the remaining block columns are loaded in front of the publish (the compiler does not move
+  // shared loads across the stores, and the multiply-adds after them should not start with a load latency)
+  constexpr int LA_PRE = 2;
+  double cpre[LA_PRE];
+#pragma unroll
+  for (int t = 0; t < LA_PRE; t++) cpre[t] = (QF + t < 2 * RP) ? cA[tx + 8 * (QF + t)] : 0.0;
+  double inv_next = 0.0;
+  const int txn = LAST ? 0 : jj + 1;
+  if (QN < 2 * RP) {
+    const double cn = cA[tx + 8 * QN];
+#pragma unroll
+    for (int p = PN; p < RP; p++) a[tr_idx(p, QN)] = fma(-r0[p], cn, a[tr_idx(p, QN)]);
+    // branch-free publish: the owners (tx = txn) write the column buffer, everybody else a scratch row that is never read,
+    // so the loads and multiply-adds below are scheduled across the stores (no divergent region in the step)
+    double* cB = (tx == txn) ? &S.col[PAR ^ 1][ty] : &S.scratch[8 + ty];
+#pragma unroll
+    for (int p = PN; p < RP; p++) cB[16 * p] = a[tr_idx(p, QN)];
+    // every thread runs the chain on its own element (it interleaves with the multiply-adds below); only the pivot's owner
+    // -- the thread with tx = txn, ty = 8 (QN & 1) + txn -- publishes the result
+    inv_next = rcp_newton(a[tr_idx(PN, QN)]);
+  }
+#pragma unroll
+  for (int q = QF; q < 2 * RP; q++) {
+    const double c = (q - QF < LA_PRE) ? cpre[q - QF < LA_PRE ? q - QF : 0] : cA[tx + 8 * q];
+#pragma unroll
+    for (int p = (q >> 1); p < RP; p++) a[tr_idx(p, q)] = fma(-r0[p], c, a[tr_idx(p, q)]);
+  }
+  if (QN < 2 * RP) {
+    const bool owner = tx == txn && ty == 8 * (QN & 1) + txn;
+    double* ib = owner ? &S.inv[PAR ^ 1] : &S.scratch[0];
+    double* pb = owner ? &S.piv[QB * 8 + 1] + jj : &S.scratch[1];
+    *ib = inv_next;
+    *pb = a[tr_idx(PN, QN)];                     // pivot j + 1 (final: steps > j leave column j + 1 alone)
+  }
+}
+
+template <int RP, int QB>
+struct RectLaBlocks {
+  static __device__ __forceinline__ void run(double (&a)[RP * (RP + 1)], RectLaSmem<RP>& S, int nact, int ty, int tx) {
+    // steps of this block column that eliminate a live column (uniform); the pair (even, odd) is unrolled so that the
+    // buffer parity is static
+    const int live = nact - QB * 8;
+    if (live <= 0) return;
+#pragma unroll 1
+    for (int jj = 0; jj < 6; jj += 2) {
+      if (jj >= live) return;
+      rect_la_step<RP, QB, false, 0>(a, S, jj, ty, tx);
+      if (jj + 1 >= live) return;
+      rect_la_step<RP, QB, false, 1>(a, S, jj + 1, ty, tx);
+    }
+    if (6 >= live) return;
+    rect_la_step<RP, QB, false, 0>(a, S, 6, ty, tx);
+    if (7 >= live) return;
+    rect_la_step<RP, QB, true, 1>(a, S, 7, ty, tx);
+    RectLaBlocks<RP, QB + 1>::run(a, S, nact, ty, tx);
+  }
+};
+template <int RP>
+struct RectLaBlocks<RP, 2 * RP> {
+  static __device__ __forceinline__ void run(double (&)[RP * (RP + 1)], RectLaSmem<RP>&, int, int, int) {}
+};
+
+// On exit S.piv[0 .. 16 RP) holds the pivots; the caller checks them (a non-positive or non-finite pivot poisons the ones
+// after it, and the pair kernel wants a flag only, so no per-step test is needed).
+template <int RP>
+__device__ __forceinline__ void rect_potrf_pivots_la(double (&a)[RP * (RP + 1)], RectLaSmem<RP>& S, int nact) {
+  const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
+  for (int t = threadIdx.x; t < 16 * RP; t += TR_THREADS) S.piv[t] = 1.0;
+  __syncthreads();
+  if (threadIdx.x == 0) { S.inv[0] = rcp_newton(a[tr_idx(0, 0)]); S.piv[0] = a[tr_idx(0, 0)]; }
+  if (tx == 0) {
+#pragma unroll
+    for (int p = 0; p < RP; p++) S.col[0][ty + 16 * p] = a[tr_idx(p, 0)];
+  }
+  RectLaBlocks<RP, 0>::run(a, S, nact, ty, tx);
+  __syncthreads();
+}
+
 }  // namespace b200gp
