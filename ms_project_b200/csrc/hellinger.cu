@@ -195,7 +195,8 @@ hellinger_pair_la_kernel(const double* __restrict__ logdet, const double* __rest
   if (fabs(ldi - ldj) > tol) {        // uniform across the CTA
     const double* Gi = G + ((size_t)mi * S + s) * n * n;
     const double* Gj = G + ((size_t)mj * S + s) * n * n;
-    const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
+    int ty, tx;
+    rect_la_coords(ty, tx);
     double a[RP * (RP + 1)];
 #pragma unroll
     for (int p = 0; p < RP; p++)

@@ -183,7 +183,6 @@ template <int RP>
 struct RectLaSmem {
   double col[2][16 * RP];     // [step parity][row]: column j as it stands when step j starts
   double inv[2];              // [step parity]: 1 / d_j
-  double scratch[16 * RP + 8]; // where the threads that do not own the next column store (never read; offset by half the banks)
   double piv[16 * RP];        // pivots d_j (1 on the padding)
 };
 
@@ -195,6 +194,20 @@ __device__ __forceinline__ double rcp_newton(double m) {
   e = fma(-m, r, 1.0);
   r = fma(r, e, r);
   return r;
+}
+
+// Thread -> (ty, tx) of the look-ahead kernel.  The shared-memory pipe is what bounds the factorisation (ncu: 90 % of its
+// wavefront peak with the plain ty = tid / 8, tx = tid % 8 map), and tools/smem_probe.cu measured what a 64-bit warp access
+// costs on sm_100a: a LOAD is one wavefront if every aligned quad of lanes touches at most two distinct 8-byte words and
+// two otherwise; a STORE is one wavefront per half warp with an active lane.  So: a quad is 2 ty x 2 tx (row operands and
+// column operands: two distinct words per quad each, one wavefront per load instead of two for the column operands), a
+// warp is 8 ty x 4 tx (a warp-wide global load of the Gram matrices covers full 32-byte sectors), and lane bit 4 is a tx
+// bit, so the eight owners of a column inside a warp sit in ONE half warp (one wavefront per published value; the plain
+// map spread the 16 owners over all four warps at two wavefronts each).
+__device__ __forceinline__ void rect_la_coords(int& ty, int& tx) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  tx = (lane & 1) | ((lane >> 4) << 1) | ((w & 1) << 2);
+  ty = ((lane >> 1) & 7) | ((w >> 1) << 3);
 }
 
 // One elimination step: column j = 8 QB + jj, PAR = j & 1 (a template argument, so every shared-memory address of the step
@@ -223,11 +236,11 @@ __device__ __forceinline__ void rect_la_step(double (&a)[RP * (RP + 1)], RectLaS
     const double cn = cA[tx + 8 * QN];
 #pragma unroll
     for (int p = PN; p < RP; p++) a[tr_idx(p, QN)] = fma(-r0[p], cn, a[tr_idx(p, QN)]);
-    // branch-free publish: the owners (tx = txn) write the column buffer, everybody else a scratch row that is never read,
-    // so the loads and multiply-adds below are scheduled across the stores (no divergent region in the step)
-    double* cB = (tx == txn) ? &S.col[PAR ^ 1][ty] : &S.scratch[8 + ty];
+    if (tx == txn) {                             // eight lanes of one half warp in two of the four warps (rect_la_coords)
+      double* cB = &S.col[PAR ^ 1][ty];
 #pragma unroll
-    for (int p = PN; p < RP; p++) cB[16 * p] = a[tr_idx(p, QN)];
+      for (int p = PN; p < RP; p++) cB[16 * p] = a[tr_idx(p, QN)];
+    }
     // every thread runs the chain on its own element (it interleaves with the multiply-adds below); only the pivot's owner
     // -- the thread with tx = txn, ty = 8 (QN & 1) + txn -- publishes the result
     inv_next = rcp_newton(a[tr_idx(PN, QN)]);
@@ -239,11 +252,10 @@ __device__ __forceinline__ void rect_la_step(double (&a)[RP * (RP + 1)], RectLaS
     for (int p = (q >> 1); p < RP; p++) a[tr_idx(p, q)] = fma(-r0[p], c, a[tr_idx(p, q)]);
   }
   if (QN < 2 * RP) {
-    const bool owner = tx == txn && ty == 8 * (QN & 1) + txn;
-    double* ib = owner ? &S.inv[PAR ^ 1] : &S.scratch[0];
-    double* pb = owner ? &S.piv[QB * 8 + 1] + jj : &S.scratch[1];
-    *ib = inv_next;
-    *pb = a[tr_idx(PN, QN)];                     // pivot j + 1 (final: steps > j leave column j + 1 alone)
+    if (tx == txn && ty == 8 * (QN & 1) + txn) {
+      S.inv[PAR ^ 1] = inv_next;
+      S.piv[QB * 8 + 1 + jj] = a[tr_idx(PN, QN)];   // pivot j + 1 (final: the steps after j leave column j + 1 alone)
+    }
   }
 }
 
@@ -277,7 +289,8 @@ struct RectLaBlocks<RP, 2 * RP> {
 // after it, and the pair kernel wants a flag only, so no per-step test is needed).
 template <int RP>
 __device__ __forceinline__ void rect_potrf_pivots_la(double (&a)[RP * (RP + 1)], RectLaSmem<RP>& S, int nact) {
-  const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
+  int ty, tx;
+  rect_la_coords(ty, tx);
   for (int t = threadIdx.x; t < 16 * RP; t += TR_THREADS) S.piv[t] = 1.0;
   __syncthreads();
   if (threadIdx.x == 0) { S.inv[0] = rcp_newton(a[tr_idx(0, 0)]); S.piv[0] = a[tr_idx(0, 0)]; }
