@@ -233,6 +233,59 @@ hellinger_pair_la_kernel(const double* __restrict__ logdet, const double* __rest
   }
 }
 
+// The same work item on the 8 x 8 thread grid (64 threads per matrix, square_potrf_pivots_la), n <= 8 NB8.
+template <int NB8, int MINB>
+__global__ void __launch_bounds__(TQ_THREADS, MINB)
+hellinger_pair_sq_kernel(const double* __restrict__ logdet, const double* __restrict__ G, int S, int n,
+                         const int* __restrict__ pair_i, const int* __restrict__ pair_j, double tol,
+                         double* __restrict__ h, int* __restrict__ hstatus) {
+  __shared__ SquareLaSmem<NB8> T;
+  const int pr = blockIdx.x, s = blockIdx.y;
+  const int mi = pair_i[pr], mj = pair_j[pr];
+  const double ldi = logdet[(size_t)mi * S + s], ldj = logdet[(size_t)mj * S + s];
+  double ldpq = ldi;
+  int bad = 0;
+  if (fabs(ldi - ldj) > tol) {        // uniform across the CTA
+    const double* Gi = G + ((size_t)mi * S + s) * n * n;
+    const double* Gj = G + ((size_t)mj * S + s) * n * n;
+    int ty, tx;
+    square_la_coords(ty, tx);
+    double a[NB8 * (NB8 + 1) / 2];
+#pragma unroll
+    for (int p = 0; p < NB8; p++)
+#pragma unroll
+      for (int q = 0; q <= p; q++) {
+        const int i = ty + 8 * p, c = tx + 8 * q;
+        double v = (i == c) ? 1.0 : 0.0;
+        if (i < n && c <= i) v = 0.5 * (__ldg(Gi + (size_t)i * n + c) + __ldg(Gj + (size_t)i * n + c));
+        a[tq_idx(p, q)] = v;
+      }
+    square_potrf_pivots_la<NB8>(a, T, n);
+    double sum = 0.0;                 // warp 0 sums log(piv[0..n)) in a fixed order and checks the pivots
+    if (threadIdx.x < 32) {
+      int badp = 0;
+#pragma unroll
+      for (int r = 0; r < (8 * NB8 + 31) / 32; r++) {
+        const int j = threadIdx.x + 32 * r;
+        if (j < n) {
+          const double pv = T.piv[j];
+          sum += log(pv);
+          badp |= (!(pv > 0.0) || !(pv < 1.7e308)) ? 1 : 0;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      bad = __any_sync(0xffffffffu, badp);
+    }
+    ldpq = sum;
+  }
+  if (threadIdx.x == 0) {
+    const double log_h = 0.25 * (ldi + ldj) - 0.5 * ldpq;
+    h[(size_t)pr * S + s] = bad ? nan("") : 1.0 - exp(log_h);
+    hstatus[(size_t)pr * S + s] = bad;
+  }
+}
+
 __global__ void hellinger_reduce_kernel(const double* __restrict__ h, const int* __restrict__ hstatus, int S, int npairs,
                                         double* __restrict__ dist, int* __restrict__ status) {
   const int pr = blockIdx.x * blockDim.x + threadIdx.x;
@@ -447,7 +500,11 @@ void launch_hellinger_pairs(const double* logdet, const double* G, int S, int n,
   static int variant = -1;
   if (variant < 0) { const char* e = getenv("B200GP_HP_VARIANT"); variant = e ? atoi(e) : 1; }
 #define HL_LAUNCH(RP, MINB) hellinger_pair_la_kernel<RP, MINB><<<grid, TR_THREADS, 0, st>>>(logdet, G, S, n, pair_i, pair_j, tol, h, hstatus)
-  if (variant == 1 && n <= 112) {
+#define HQ_LAUNCH(NB8, MINB) hellinger_pair_sq_kernel<NB8, MINB><<<grid, TQ_THREADS, 0, st>>>(logdet, G, S, n, pair_i, pair_j, tol, h, hstatus)
+  if (variant == 2 && n > 96 && n <= 104) HQ_LAUNCH(13, 4);
+  else if (variant == 2 && n > 80 && n <= 96) HQ_LAUNCH(12, 4);
+  else
+  if (variant >= 1 && n <= 112) {
     if (n <= 64) HL_LAUNCH(4, 6);
     else if (n <= 80) HL_LAUNCH(5, 4);
     else if (n <= 96) HL_LAUNCH(6, 3);

@@ -302,4 +302,110 @@ __device__ __forceinline__ void rect_potrf_pivots_la(double (&a)[RP * (RP + 1)],
   __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------------
+// The look-ahead factorisation on an 8 x 8 thread grid (64 threads, two warps per matrix): thread (ty, tx) owns the
+// elements (ty + 8 p, tx + 8 q), q <= p < NB8 -- NB8 (NB8 + 1) / 2 doubles, 91 for NB8 = 13 (n <= 104).  Against the 16 x 8
+// grid: 8 x 8 blocks waste less on the dead part of the diagonal blocks and of the block column being eliminated (executed
+// / algorithmic multiply-adds 1.40 instead of 1.88), and a thread does up to NB8 (NB8 + 1) / 2 multiply-adds per 2 NB8
+// operand loads, so a matrix costs about half the instructions and half the shared-memory wavefronts.  The price is the
+// register file: ~230 registers per thread, four CTAs = eight warps per SM.
+// ------------------------------------------------------------------------------------------------
+constexpr int TQ_THREADS = 64;
+
+template <int NB8>
+struct SquareLaSmem {
+  double col[2][8 * NB8];
+  double inv[2];
+  double piv[8 * NB8];
+};
+
+__host__ __device__ constexpr int tq_idx(int p, int q) { return p * (p + 1) / 2 + q; }    // block (p, q), q <= p
+
+// lane bits (low to high): tx0, ty0, ty1, ty2, tx1; warp bit: tx2 -- see rect_la_coords for the rules behind it
+__device__ __forceinline__ void square_la_coords(int& ty, int& tx) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  tx = (lane & 1) | ((lane >> 4) << 1) | (w << 2);
+  ty = (lane >> 1) & 7;
+}
+
+template <int NB8, int B, bool LAST, int PAR>
+__device__ __forceinline__ void square_la_step(double (&a)[NB8 * (NB8 + 1) / 2], SquareLaSmem<NB8>& S, int jj, int ty, int tx) {
+  constexpr int QN = LAST ? B + 1 : B;           // block column (= block row) of column j + 1
+  constexpr int QF = QN + 1 > B + 1 ? QN + 1 : B + 1;   // first block column of the remaining update
+  const double* cA = S.col[PAR];
+  __syncthreads();
+  const double i0 = S.inv[PAR];
+  double r0[NB8];
+#pragma unroll
+  for (int p = B; p < NB8; p++) r0[p] = cA[ty + 8 * p] * i0;
+  constexpr int LA_PRE = 2;
+  double cpre[LA_PRE];
+#pragma unroll
+  for (int t = 0; t < LA_PRE; t++) cpre[t] = (QF + t < NB8) ? cA[tx + 8 * (QF + t)] : 0.0;
+  double inv_next = 0.0;
+  const int txn = LAST ? 0 : jj + 1;
+  if (QN < NB8) {
+    const double cn = cA[tx + 8 * QN];
+#pragma unroll
+    for (int p = QN; p < NB8; p++) a[tq_idx(p, QN)] = fma(-r0[p], cn, a[tq_idx(p, QN)]);
+    if (tx == txn) {
+      double* cB = &S.col[PAR ^ 1][ty];
+#pragma unroll
+      for (int p = QN; p < NB8; p++) cB[8 * p] = a[tq_idx(p, QN)];
+    }
+    inv_next = rcp_newton(a[tq_idx(QN, QN)]);
+  }
+#pragma unroll
+  for (int q = QF; q < NB8; q++) {
+    const double c = (q - QF < LA_PRE) ? cpre[q - QF < LA_PRE ? q - QF : 0] : cA[tx + 8 * q];
+#pragma unroll
+    for (int p = q; p < NB8; p++) a[tq_idx(p, q)] = fma(-r0[p], c, a[tq_idx(p, q)]);
+  }
+  if (QN < NB8) {
+    if (tx == txn && ty == txn) {
+      S.inv[PAR ^ 1] = inv_next;
+      S.piv[B * 8 + 1 + jj] = a[tq_idx(QN, QN)];
+    }
+  }
+}
+
+template <int NB8, int B>
+struct SquareLaBlocks {
+  static __device__ __forceinline__ void run(double (&a)[NB8 * (NB8 + 1) / 2], SquareLaSmem<NB8>& S, int nact, int ty, int tx) {
+    const int live = nact - B * 8;
+    if (live <= 0) return;
+#pragma unroll 1
+    for (int jj = 0; jj < 6; jj += 2) {
+      if (jj >= live) return;
+      square_la_step<NB8, B, false, 0>(a, S, jj, ty, tx);
+      if (jj + 1 >= live) return;
+      square_la_step<NB8, B, false, 1>(a, S, jj + 1, ty, tx);
+    }
+    if (6 >= live) return;
+    square_la_step<NB8, B, false, 0>(a, S, 6, ty, tx);
+    if (7 >= live) return;
+    square_la_step<NB8, B, true, 1>(a, S, 7, ty, tx);
+    SquareLaBlocks<NB8, B + 1>::run(a, S, nact, ty, tx);
+  }
+};
+template <int NB8>
+struct SquareLaBlocks<NB8, NB8> {
+  static __device__ __forceinline__ void run(double (&)[NB8 * (NB8 + 1) / 2], SquareLaSmem<NB8>&, int, int, int) {}
+};
+
+template <int NB8>
+__device__ __forceinline__ void square_potrf_pivots_la(double (&a)[NB8 * (NB8 + 1) / 2], SquareLaSmem<NB8>& S, int nact) {
+  int ty, tx;
+  square_la_coords(ty, tx);
+  for (int t = threadIdx.x; t < 8 * NB8; t += TQ_THREADS) S.piv[t] = 1.0;
+  __syncthreads();
+  if (tx == 0 && ty == 0) { S.inv[0] = rcp_newton(a[0]); S.piv[0] = a[0]; }
+  if (tx == 0) {
+#pragma unroll
+    for (int p = 0; p < NB8; p++) S.col[0][ty + 8 * p] = a[tq_idx(p, 0)];
+  }
+  SquareLaBlocks<NB8, 0>::run(a, S, nact, ty, tx);
+  __syncthreads();
+}
+
 }  // namespace b200gp
