@@ -6,7 +6,6 @@
 //   pairs:       per (pair, sample s)   if |ld_i - ld_j| > tol: logdet(1/2 (G_i,s + G_j,s)) else ld_i
 //                                        h_s = 1 - exp(1/4 (ld_i + ld_j) - 1/2 logdet_pq);  d = sqrt(clip(mean_s h_s, 0, 1))
 // Each small factorisation (n <= 128) is one CTA running the in-register Cholesky of tile_potrf.cuh.
-#include <cstdlib>
 #include "kernels.cuh"
 #include "kprog.cuh"
 #include "tile_potrf.cuh"
@@ -132,53 +131,6 @@ hellinger_pair_kernel(const double* __restrict__ logdet, const double* __restric
   }
 }
 
-// The same work item on the 16 x 8 thread grid of rect_potrf_pivots (128 threads per matrix).
-template <int RP, int MINB>
-__global__ void __launch_bounds__(TR_THREADS, MINB)
-hellinger_pair_rect_kernel(const double* __restrict__ logdet, const double* __restrict__ G, int S, int n,
-                           const int* __restrict__ pair_i, const int* __restrict__ pair_j, double tol,
-                           double* __restrict__ h, int* __restrict__ hstatus) {
-  __shared__ RectPotrfSmem<RP> T;
-  const int pr = blockIdx.x, s = blockIdx.y;
-  const int mi = pair_i[pr], mj = pair_j[pr];
-  const double ldi = logdet[(size_t)mi * S + s], ldj = logdet[(size_t)mj * S + s];
-  double ldpq = ldi;
-  int bad = 0;
-  if (fabs(ldi - ldj) > tol) {        // uniform across the CTA
-    const double* Gi = G + ((size_t)mi * S + s) * n * n;
-    const double* Gj = G + ((size_t)mj * S + s) * n * n;
-    const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
-    double a[RP * (RP + 1)];
-#pragma unroll
-    for (int p = 0; p < RP; p++)
-#pragma unroll
-      for (int q = 0; q <= 2 * p + 1; q++) {
-        const int i = ty + 16 * p, c = tx + 8 * q;
-        double v = (i == c) ? 1.0 : 0.0;
-        if (i < n && c <= i) v = 0.5 * (__ldg(Gi + (size_t)i * n + c) + __ldg(Gj + (size_t)i * n + c));
-        a[tr_idx(p, q)] = v;
-      }
-    rect_potrf_pivots<RP>(a, T, n);
-    double sum = 0.0;                 // warp 0 sums log(piv[0..n)) in a fixed order
-    if (threadIdx.x < 32) {
-#pragma unroll
-      for (int r = 0; r < (16 * RP + 31) / 32; r++) {
-        const int j = threadIdx.x + 32 * r;
-        if (j < n) sum += log(T.piv[j]);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    }
-    ldpq = sum;
-    bad = T.fail != 0;
-  }
-  if (threadIdx.x == 0) {
-    const double log_h = 0.25 * (ldi + ldj) - 0.5 * ldpq;
-    h[(size_t)pr * S + s] = bad ? nan("") : 1.0 - exp(log_h);
-    hstatus[(size_t)pr * S + s] = bad;
-  }
-}
-
 // The same work item on the look-ahead factorisation (rect_potrf_pivots_la: next column and its pivot reciprocal published
 // under the trailing update, one reciprocal per step and matrix).
 template <int RP, int MINB>
@@ -250,6 +202,9 @@ hellinger_pair_sq_kernel(const double* __restrict__ logdet, const double* __rest
     const double* Gj = G + ((size_t)mj * S + s) * n * n;
     int ty, tx;
     square_la_coords(ty, tx);
+    // (Measured on C3 and not kept: staging G_j through cp.async into per-thread shared-memory columns so that both
+    // operands are in flight at once -- 0.119 s against 0.102 s; L1 prefetches of both operands in front of the loads --
+    // 0.112 s.  The load phase is 25 % of a warp's life in ncu, but the other three CTAs of the SM compute meanwhile.)
     double a[NB8 * (NB8 + 1) / 2];
 #pragma unroll
     for (int p = 0; p < NB8; p++)
@@ -472,6 +427,7 @@ void launch_hpair_finish(const double* logdet, int S, const int* pair_i, const i
 int configure_hellinger_kernels() {
   cudaError_t e = cudaFuncSetAttribute(hellinger_precompute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(HellSmem));
+  if (e != cudaSuccess) return (int)e;
   return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -488,34 +444,27 @@ void launch_hellinger_pairs(const double* logdet, const double* G, int S, int n,
                             int npairs, double tol, double* h, int* hstatus, double* dist, int* status, cudaStream_t st) {
   dim3 grid(npairs, S);               // x = pair (fastest), y = sample: sample-major execution order, see the kernel
 #define HP_LAUNCH(R, MINB, COLS) hellinger_pair_kernel<R, MINB, COLS><<<grid, TS_THREADS, 0, st>>>(logdet, G, S, n, pair_i, pair_j, tol, h, hstatus)
-#define HR_LAUNCH(RP, MINB) hellinger_pair_rect_kernel<RP, MINB><<<grid, TR_THREADS, 0, st>>>(logdet, G, S, n, pair_i, pair_j, tol, h, hstatus)
   // Measured on C3 (124 750 pairs x 20 samples, n = 100; round 1's kernel: 0.369 s):
   //   16 x 16 thread grid (256 threads): one column per barrier, three CTAs per SM 0.224 s; two columns per barrier 0.245 s
   //     (three CTAs, 80 B of spills) / 0.273 s (two CTAs); pivot reciprocal by its owner in front of the barrier 0.25-0.29 s
-  //   16 x 8 thread grid (128 threads, 167 registers): three CTAs per SM 0.187 s (kept), two CTAs 0.242 s
+  //   16 x 8 thread grid (128 threads, 167 registers, three CTAs per SM) 0.185 s
+  //     + look-ahead (next column and its pivot reciprocal published under the trailing update, scaled row operands) 0.167 s
+  //     + static buffer parity, pivot test after the factorisation (91 -> 73 instructions per step) 0.148 s
+  //     + lane map for one-wavefront shared-memory accesses (ncu: the shared-memory pipe was 90 % busy) 0.130 s
+  //   8 x 8 thread grid (64 threads, 240 registers, four CTAs per SM), same look-ahead and lane rules 0.102 s (kept)
+  //     with G_j staged by cp.async 0.119 s, with L1 prefetches of both operands 0.112 s (not kept)
   //   DMMA formulation (8 x 8 accumulator tiles over 4 or 8 warps, 13 panel steps): correct, 0.218-0.279 s, 47 % of its
   //     stall samples behind the three barriers of a panel step; removed (profiles/experiments/)
-  // Occupancy decides every comparison: the kernel is bound by the latency chain of an elimination step (barrier -> pivot
-  // -> reciprocal -> scaled column -> multiply-adds), which only other resident matrices can hide.
-  static int variant = -1;
-  if (variant < 0) { const char* e = getenv("B200GP_HP_VARIANT"); variant = e ? atoi(e) : 1; }
 #define HL_LAUNCH(RP, MINB) hellinger_pair_la_kernel<RP, MINB><<<grid, TR_THREADS, 0, st>>>(logdet, G, S, n, pair_i, pair_j, tol, h, hstatus)
 #define HQ_LAUNCH(NB8, MINB) hellinger_pair_sq_kernel<NB8, MINB><<<grid, TQ_THREADS, 0, st>>>(logdet, G, S, n, pair_i, pair_j, tol, h, hstatus)
-  if (variant == 2 && n > 96 && n <= 104) HQ_LAUNCH(13, 4);
-  else if (variant == 2 && n > 80 && n <= 96) HQ_LAUNCH(12, 4);
-  else
-  if (variant >= 1 && n <= 112) {
-    if (n <= 64) HL_LAUNCH(4, 6);
-    else if (n <= 80) HL_LAUNCH(5, 4);
-    else if (n <= 96) HL_LAUNCH(6, 3);
-    else HL_LAUNCH(7, 3);
-  } else
-  if (n <= 64) HR_LAUNCH(4, 6);
-  else if (n <= 80) HR_LAUNCH(5, 4);
-  else if (n <= 96) HR_LAUNCH(6, 3);
-  else if (n <= 112) HR_LAUNCH(7, 3);
+  if (n <= 64) HQ_LAUNCH(8, 8);
+  else if (n <= 80) HQ_LAUNCH(10, 6);
+  else if (n <= 96) HQ_LAUNCH(12, 4);
+  else if (n <= 104) HQ_LAUNCH(13, 4);
+  else if (n <= 112) HL_LAUNCH(7, 3);
   else HP_LAUNCH(8, 2, 2);
-#undef HR_LAUNCH
+#undef HL_LAUNCH
+#undef HQ_LAUNCH
 #undef HP_LAUNCH
   g_launch_count++;
   hellinger_reduce_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(h, hstatus, S, npairs, dist, status);

@@ -118,55 +118,11 @@ namespace b200gp {
 // ------------------------------------------------------------------------------------------------
 constexpr int TR_THREADS = 128;
 
-template <int RP>
-struct RectPotrfSmem {
-  double col[2][16 * RP];     // [step parity][row]
-  double piv[16 * RP];
-  int fail;
-};
-
 __host__ __device__ constexpr int tr_idx(int p, int q) { return p * (p + 1) + q; }    // block (p, q), q <= 2 p + 1
 
-template <int RP>
-__device__ __forceinline__ void rect_potrf_pivots(double (&a)[RP * (RP + 1)], RectPotrfSmem<RP>& S, int nact) {
-  const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
-  if (threadIdx.x == 0) S.fail = 0;
-  for (int t = threadIdx.x; t < 16 * RP; t += TR_THREADS) S.piv[t] = 1.0;
-#pragma unroll
-  for (int qb = 0; qb < 2 * RP; qb++) {         // block column of 8 matrix columns
-    const int pb = qb >> 1;                     // first block row with live elements in these columns
-#pragma unroll 1
-    for (int jj = 0; jj < 8; jj++) {
-      const int j = qb * 8 + jj;
-      if (j >= nact) break;                     // uniform
-      double* cA = S.col[j & 1];
-      if (tx == jj) {
-#pragma unroll
-        for (int p = pb; p < RP; p++) cA[ty + 16 * p] = a[tr_idx(p, qb)];
-      }
-      __syncthreads();
-      const double d0 = cA[j];
-      const double i0 = 1.0 / d0;
-      if (threadIdx.x == 0) {
-        S.piv[j] = d0;
-        if ((!(d0 > 0.0) || !(d0 < 1.7e308)) && S.fail == 0) S.fail = j + 1;
-      }
-      double c0[2 * RP];
-#pragma unroll
-      for (int q = qb; q < 2 * RP; q++) c0[q] = cA[tx + 8 * q] * i0;
-#pragma unroll
-      for (int p = pb; p < RP; p++) {
-        const double r0 = cA[ty + 16 * p];
-#pragma unroll
-        for (int q = qb; q <= 2 * p + 1; q++) a[tr_idx(p, q)] = fma(-r0, c0[q], a[tr_idx(p, q)]);
-      }
-    }
-  }
-  __syncthreads();
-}
-
 // ------------------------------------------------------------------------------------------------
-// Look-ahead form of the 16 x 8 factorisation (the one the pair kernel runs).  Per elimination step j the chain
+// Look-ahead form of the 16 x 8 factorisation (the pair kernel runs it for 104 < n <= 112; the 8 x 8 grid at the end of the
+// file serves the orders below).  Per elimination step j the chain
 // barrier -> pivot -> reciprocal -> scaled operands -> multiply-adds -> publish column j + 1 -> barrier is what bounds the
 // kernel (ncu: FP64 pipe 37 % busy, issue slots 44 %), so everything that can leave it does:
 //   * the block column that holds column j + 1 is updated FIRST, and its owners publish column j + 1 (into the other

@@ -77,10 +77,10 @@ def test_precompute_and_distances_match_oracle():
     assert abs(d01 ** 2 - D_ref[0, 5] ** 2) < 1e-7
 
 
-@pytest.mark.parametrize('n', [17, 64, 65, 80, 96, 97, 112, 113, 128])
+@pytest.mark.parametrize('n', [17, 64, 65, 80, 81, 96, 97, 104, 105, 112, 113, 128])
 def test_pair_distances_at_every_subset_size_class(n):
-    """The pair kernel is instantiated per size class (16-row block counts 4 ... 8, two thread grids): every class, at its
-    edges, against the oracle."""
+    """The pair kernel is instantiated per size class (8 x 8 thread grid with 8, 10, 12, 13 block rows up to n = 104, the
+    16 x 8 grid up to 112, the 16 x 16 grid up to 128): every class, at its edges, against the oracle."""
     rng = np.random.default_rng(n)
     x = rng.random((n, 3))
     x = (x - x.mean(0)) / x.std(0)
