@@ -27,7 +27,7 @@ $C5 > $O/c5_$TAG.log 2>&1
 cap c5upd chol_update64_tma_kernel 4 $C5          # the first K = 512 trailing update of the N = 16384 Cholesky (29 040 CTAs)
 C3="python tools/bench_configs.py --configs c3 --cpu-budget 0"
 $C3 > $O/c3_$TAG.log 2>&1
-cap hpair hellinger_pair_kernel 1 $C3
+cap hpair hellinger_pair 1 $C3
 cap hpre hellinger_precompute_kernel 0 $C3
 python bench.py --steps 5 --warmup 3 > $O/bench_$TAG.json 2> $O/bench_$TAG.err
 tail -c 400 $O/bench_$TAG.json

@@ -36,6 +36,8 @@ KEYS = [
     ('smsp__sass_thread_inst_executed_op_dfma_pred_on.sum', 'DFMA thread-instructions'),
     ('smsp__sass_thread_inst_executed_op_dmul_pred_on.sum', 'DMUL thread-instructions'),
     ('smsp__sass_thread_inst_executed_op_dadd_pred_on.sum', 'DADD thread-instructions'),
+    ('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'L1 / shared-memory data pipe (wavefronts) % of peak'),
+    ('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'shared-memory wavefronts'),
     ('dram__bytes_read.sum', 'DRAM read'),
     ('dram__bytes_write.sum', 'DRAM write'),
     ('dram__throughput.avg.pct_of_peak_sustained_elapsed', 'DRAM throughput % of peak'),
