@@ -55,7 +55,7 @@ __device__ void compile_one(const Batch& b, int slot) {
   const int t0 = b.prog_off[item], nt = b.prog_off[item + 1] - t0;
   CProg& cp = b.cprog[slot];
   cp.nparam = b.theta_off[item + 1] - b.theta_off[item] - 1;
-  cp.pad = 0;
+  cp.shape = -1;
   int L = 0, G = 0, single = 0, kind = CK_GENERIC;
   if (nt <= CP_MAXTOK) {
     unsigned char masks[CP_MAXTOK][CP_GMAX];
@@ -96,6 +96,53 @@ __device__ void compile_one(const Batch& b, int slot) {
   }
   for (int i = L; i < CP_LMAX; i++) cp.leaf[i] = make_int4(OP_CONST, 0, 0, 0);
   for (int i = G; i < 24; i++) cp.term[i] = 0;
+  cp.shape = -1;
+  if (kind == CK_POLY4) {       // relabel the leaves so that the term set is one of the canonical shapes (cprog.cuh)
+    int found = -1, fperm = 0;
+    for (int pi = 0; pi < 24 && found < 0; pi++) {
+      // pi-th permutation of {0, 1, 2, 3} (factorial number system): perm[i] = new slot of leaf i
+      int perm[4], pool[4] = {0, 1, 2, 3}, code = pi;
+      for (int i = 0, f = 6; i < 4; i++) {
+        const int d = code / f;
+        code %= f;
+        perm[i] = pool[d];
+        for (int t = d; t < 3 - i; t++) pool[t] = pool[t + 1];
+        if (i < 2) f /= (3 - i);
+      }
+      unsigned m[4] = {0, 0, 0, 0};
+      bool inside = true;
+      for (int g = 0; g < 4; g++)
+        if (g < G) {
+          for (int i = 0; i < 4; i++)
+            if (cp.term[g] & (1u << i)) { m[g] |= 1u << perm[i]; if (perm[i] >= L) inside = false; }
+        }
+      if (!inside || G > 4) continue;
+      for (int x = 0; x < G; x++)            // sort ascending (G <= 4)
+        for (int y = x + 1; y < G; y++)
+          if (m[y] < m[x]) { const unsigned t = m[x]; m[x] = m[y]; m[y] = t; }
+      const unsigned key = m[0] | (m[1] << 4) | (m[2] << 8) | (m[3] << 12);
+      for (int sidx = 0; sidx < CP_NSHAPES; sidx++)
+        if (cp_shape_leaves(sidx) == L && cp_shape_key(sidx) == key) { found = sidx; fperm = pi; }
+    }
+    if (found >= 0) {
+      int perm[4], pool[4] = {0, 1, 2, 3}, code = fperm;
+      for (int i = 0, f = 6; i < 4; i++) {
+        const int d = code / f;
+        code %= f;
+        perm[i] = pool[d];
+        for (int t = d; t < 3 - i; t++) pool[t] = pool[t + 1];
+        if (i < 2) f /= (3 - i);
+      }
+      int4 old[4];
+      for (int i = 0; i < 4; i++) old[i] = cp.leaf[i];
+      for (int i = 0; i < L; i++) cp.leaf[perm[i]] = old[i];
+      const unsigned key = cp_shape_key(found);
+      for (int g = 0; g < 4; g++) cp.term[g] = (unsigned char)((key >> (4 * g)) & 15u);
+      cp.shape = found;
+    } else {
+      kind = CK_POLY8;          // not reachable for +/* trees over distinct leaves; the generic term loop handles it anyway
+    }
+  }
   cp.kind = kind; cp.L = L; cp.G = G; cp.single = single;
 }
 
@@ -370,6 +417,55 @@ __device__ __forceinline__ void mask_product(const double (&v)[LMAX][E], unsigne
   }
 }
 
+// K and the adjoints dK/dv_l of the canonical <= 4-leaf shapes (cprog.cuh), in factored form: one switch per row step.
+#define SH_ALL(expr) _Pragma("unroll") for (int e = 0; e < E; e++) { const double a = v[0][e], b = v[1][e], c = v[2][e], d = v[3][e]; (void)a; (void)b; (void)c; (void)d; expr; }
+template <int E>
+__device__ __forceinline__ void shape_value(int shape, const double (&v)[4][E], double (&k)[E]) {
+  switch (shape) {
+    case 0:  SH_ALL(k[e] = a) break;
+    case 1:  SH_ALL(k[e] = a + b) break;
+    case 2:  SH_ALL(k[e] = a * b) break;
+    case 3:  SH_ALL(k[e] = (a + b) + c) break;
+    case 4:  SH_ALL(k[e] = fma(b, c, a)) break;
+    case 5:  SH_ALL(k[e] = a * (b + c)) break;
+    case 6:  SH_ALL(k[e] = (a * b) * c) break;
+    case 7:  SH_ALL(k[e] = (a + b) + (c + d)) break;
+    case 8:  SH_ALL(k[e] = fma(c, d, a + b)) break;
+    case 9:  SH_ALL(k[e] = fma(b, c + d, a)) break;
+    case 10: SH_ALL(k[e] = fma(b * c, d, a)) break;
+    case 11: SH_ALL(k[e] = a * ((b + c) + d)) break;
+    case 12: SH_ALL(k[e] = (a + d) * (b + c)) break;
+    case 13: SH_ALL(k[e] = fma(a, b, c * d)) break;
+    case 14: SH_ALL(k[e] = a * fma(c, d, b)) break;
+    case 15: SH_ALL(k[e] = (a * b) * (c + d)) break;
+    default: SH_ALL(k[e] = (a * b) * (c * d)) break;
+  }
+}
+
+// g[l][e] = w[e] * dK/dv_l
+template <int E>
+__device__ __forceinline__ void shape_adjoints(int shape, const double (&v)[4][E], const double (&w)[E], double (&g)[4][E]) {
+#define SH_G(g0, g1, g2, g3) SH_ALL(g[0][e] = g0; g[1][e] = g1; g[2][e] = g2; g[3][e] = g3)
+  switch (shape) {
+    case 0: case 1: case 3: case 7: SH_G(w[e], w[e], w[e], w[e]) break;                     // pure sums
+    case 2:  SH_G(w[e] * b, w[e] * a, 0.0, 0.0) break;
+    case 4:  SH_G(w[e], w[e] * c, w[e] * b, 0.0) break;
+    case 5:  { SH_ALL(const double wa = w[e] * a; g[0][e] = w[e] * (b + c); g[1][e] = wa; g[2][e] = wa; g[3][e] = 0.0) } break;
+    case 6:  { SH_ALL(const double wc = w[e] * c; g[0][e] = wc * b; g[1][e] = wc * a; g[2][e] = w[e] * (a * b); g[3][e] = 0.0) } break;
+    case 8:  SH_G(w[e], w[e], w[e] * d, w[e] * c) break;
+    case 9:  { SH_ALL(const double wb = w[e] * b; g[0][e] = w[e]; g[1][e] = w[e] * (c + d); g[2][e] = wb; g[3][e] = wb) } break;
+    case 10: { SH_ALL(const double wd = w[e] * d; g[0][e] = w[e]; g[1][e] = wd * c; g[2][e] = wd * b; g[3][e] = w[e] * (b * c)) } break;
+    case 11: { SH_ALL(const double wa = w[e] * a; g[0][e] = w[e] * ((b + c) + d); g[1][e] = wa; g[2][e] = wa; g[3][e] = wa) } break;
+    case 12: { SH_ALL(const double wt_ = w[e] * (b + c); const double ws = w[e] * (a + d); g[0][e] = wt_; g[1][e] = ws; g[2][e] = ws; g[3][e] = wt_) } break;
+    case 13: SH_G(w[e] * b, w[e] * a, w[e] * d, w[e] * c) break;
+    case 14: { SH_ALL(const double wa = w[e] * a; g[0][e] = w[e] * fma(c, d, b); g[1][e] = wa; g[2][e] = wa * d; g[3][e] = wa * c) } break;
+    case 15: { SH_ALL(const double wt_ = w[e] * (c + d); const double wab = w[e] * (a * b); g[0][e] = wt_ * b; g[1][e] = wt_ * a; g[2][e] = wab; g[3][e] = wab) } break;
+    default: { SH_ALL(const double wab = w[e] * (a * b); const double wcd = w[e] * (c * d); g[0][e] = wcd * b; g[1][e] = wcd * a; g[2][e] = wab * d; g[3][e] = wab * c) } break;
+  }
+#undef SH_G
+}
+#undef SH_ALL
+
 // product-term masks: 4 leaf slots expand to at most 4 terms (one register); 8 slots read shared memory
 template <int LMAX>
 __device__ __forceinline__ unsigned term_mask(unsigned terms4, unsigned term_addr, int g) {
@@ -398,7 +494,7 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? POLY_BUILD_CTAS : 2) poly_bui
     int ops[LMAX];
     poly_prologue<LMAX>(S, b, slot, ti, tj, c, Aj, Sj, Cj, ops);
     __syncthreads();
-    const int L = S.cp.L, G = S.cp.G;
+    const int L = S.cp.L, G = S.cp.G, shape = S.cp.shape;
     const unsigned terms4 = *reinterpret_cast<const unsigned*>(S.cp.term);
     const double diag_add = b.add_diag == 1 ? S.noise + EXACT_INFERENCE_JITTER + (b.jitter ? b.jitter[slot] : 0.0)
                                              : (b.add_diag == 2 ? S.noise : 0.0);
@@ -415,16 +511,23 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? POLY_BUILD_CTAS : 2) poly_bui
           lds_rows<E>(sb + (unsigned)offsetof(SM, Ai) + (l * NB + r0) * 8, Ar);
           leaf_fwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, sb + (unsigned)offsetof(SM, etab), Ar, sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8,
                       sb + (unsigned)offsetof(SM, Ci) + (l * NB + r0) * 8, Aj[l], Sj[l], Cj[l], v[l], aux);
+        } else if (LMAX == 4) {
+#pragma unroll
+          for (int e = 0; e < E; e++) v[l][e] = 0.0;       // the shape formulas name all four slots
         }
       double k[E];
+      if constexpr (LMAX == 4) {
+        shape_value<E>(shape, v, k);
+      } else {
 #pragma unroll
-      for (int e = 0; e < E; e++) k[e] = 0.0;
-      for (int g = 0; g < G; g++) {
-        const unsigned mask = term_mask<LMAX>(terms4, sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), g);
-        double p[E];
-        mask_product<LMAX, E>(v, mask, p);
+        for (int e = 0; e < E; e++) k[e] = 0.0;
+        for (int g = 0; g < G; g++) {
+          const unsigned mask = term_mask<LMAX>(terms4, sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), g);
+          double p[E];
+          mask_product<LMAX, E>(v, mask, p);
 #pragma unroll
-        for (int e = 0; e < E; e++) k[e] += p[e];
+          for (int e = 0; e < E; e++) k[e] += p[e];
+        }
       }
       if (interior) {        // tile strictly below the diagonal and inside N: no padding, no diagonal element
 #pragma unroll
@@ -475,26 +578,11 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
   }
   const double aj = b.alpha[(size_t)slot * b.Np + tj * NB + col0 + c];
   __syncthreads();
-  const int L = S.cp.L, G = S.cp.G, single = S.cp.single;
+  const int L = S.cp.L, G = S.cp.G, single = S.cp.single, shape = S.cp.shape;
   const unsigned terms4 = *reinterpret_cast<const unsigned*>(S.cp.term);
   double acc[LMAX][3], accn = 0.0;
 #pragma unroll
   for (int l = 0; l < LMAX; l++) { acc[l][0] = 0.0; acc[l][1] = 0.0; acc[l][2] = 0.0; }
-  // <= 4 leaves: adjm[l] packs, one byte each, the terms containing leaf l with l's bit cleared and bit 4 set as a
-  // presence marker (a term that is the leaf alone has no other bit), so the row loop walks exactly the terms it needs
-  unsigned adjm[LMAX == 4 ? 4 : 1];
-  if (LMAX == 4) {
-#pragma unroll
-    for (int l = 0; l < 4; l++) {
-      unsigned packed = 0u;
-      int n = 0;
-      for (int t = 0; t < G; t++) {
-        const unsigned mask = (terms4 >> (8 * t)) & 0xffu;
-        if (mask & (1u << l)) { packed |= ((mask & ~(1u << l)) | 16u) << (8 * n); n++; }
-      }
-      adjm[l] = packed;
-    }
-  }
   const double* Kinv = Kt + c;
   const int gj = tj * NB + col0 + c;
   // diagonal tiles: rows above this warp's first column hold no lower-triangle element
@@ -534,26 +622,27 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
         lds_rows<E>(sb + (unsigned)offsetof(SM, Ai) + (l * NB + r0) * 8, Ar);
         leaf_fwd<E>(ops[l], sb + (unsigned)offsetof(SM, cst) + l * 32, sb + (unsigned)offsetof(SM, etab), Ar, sb + (unsigned)offsetof(SM, Si) + (l * NB + r0) * 8,
                     sb + (unsigned)offsetof(SM, Ci) + (l * NB + r0) * 8, Aj[l], Sj[l], Cj[l], v[l], aux[l]);
+      } else if (LMAX == 4) {
+#pragma unroll
+        for (int e = 0; e < E; e++) v[l][e] = 0.0;         // the shape formulas name all four slots
       }
+    double g4[LMAX == 4 ? 4 : 1][E];
+    if constexpr (LMAX == 4) shape_adjoints<E>(shape, v, wt, g4);
 #pragma unroll
     for (int l = 0; l < LMAX; l++)
       if (l < L) {
         double g[E];
-        if (single) {
+        if constexpr (LMAX == 4) {
+#pragma unroll
+          for (int e = 0; e < E; e++) g[e] = g4[l][e];
+        } else if (single) {
 #pragma unroll
           for (int e = 0; e < E; e++) g[e] = wt[e];
         } else {
           double adj[E];
 #pragma unroll
           for (int e = 0; e < E; e++) adj[e] = 0.0;
-          if (LMAX == 4) {        // per-leaf list of the terms that contain the leaf, with the leaf removed: built once per tile
-            for (unsigned m = adjm[l]; m != 0u; m >>= 8) {
-              double p[E];
-              mask_product<LMAX, E>(v, (m & 0xffu) & 15u, p);
-#pragma unroll
-              for (int e = 0; e < E; e++) adj[e] += p[e];
-            }
-          } else {
+          {
             for (int t = 0; t < G; t++) {
               const unsigned mask = term_mask<LMAX>(terms4, sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), t);
               if (!(mask & (1u << l))) continue;
