@@ -237,10 +237,12 @@ __device__ __forceinline__ void leaf_fwd(int op, unsigned cst, unsigned etab, co
                                          double Aj, double Sj, double Cj, double (&v)[E], double (&aux)[E]) {
   double c0, c1;
   lds_v2(cst, c0, c1);
-  if (op == OP_SE) {            // rbf.ipynb#1-2: v exp(-r^2 / 2)
+  switch (op) {
+  case OP_SE: {            // rbf.ipynb#1-2: v exp(-r^2 / 2)
 #pragma unroll
     for (int e = 0; e < E; e++) { const double r = (Ar[e] - Aj) * c1; const double a = r * r; aux[e] = a; v[e] = c0 * exp_tab(-0.5 * a, etab); }
-  } else if (op == OP_RQ) {     // rational-quadratic.ipynb#2: v exp(-a log1p(r^2 / 2a))
+  } break;
+  case OP_RQ: {     // rational-quadratic.ipynb#2: v exp(-a log1p(r^2 / 2a))
     double c2, c3;
     lds_v2(cst + 16, c2, c3);
 #pragma unroll
@@ -250,7 +252,8 @@ __device__ __forceinline__ void leaf_fwd(int op, unsigned cst, unsigned etab, co
       aux[e] = lg;
       v[e] = c0 * exp_tab(-c2 * lg, etab);
     }
-  } else if (op == OP_PER) {    // periodic.ipynb#2: v exp(-2 sin^2(pi (x - x') / p) / l^2); sin(a_i - a_j) by the angle-difference identity
+  } break;
+  case OP_PER: {    // periodic.ipynb#2: v exp(-2 sin^2(pi (x - x') / p) / l^2); sin(a_i - a_j) by the angle-difference identity
     const double il = lds_f64(cst + 16);
     double Sr[E], Cr[E];
     lds_rows<E>(srow, Sr);
@@ -262,12 +265,15 @@ __device__ __forceinline__ void leaf_fwd(int op, unsigned cst, unsigned etab, co
       aux[e] = s;
       v[e] = c0 * exp_tab(-2.0 * (q * q), etab);
     }
-  } else if (op == OP_LIN) {    // linear.ipynb#2: v (x - c)(x' - c)
+  } break;
+  case OP_LIN: {    // linear.ipynb#2: v (x - c)(x' - c)
 #pragma unroll
     for (int e = 0; e < E; e++) { aux[e] = Ar[e] * Aj; v[e] = c0 * aux[e]; }
-  } else {
+  } break;
+  default: {
 #pragma unroll
     for (int e = 0; e < E; e++) { aux[e] = 0.0; v[e] = c0; }
+  } break;
   }
 }
 
@@ -277,14 +283,16 @@ template <int E>
 __device__ __forceinline__ void leaf_bwd(int op, unsigned cst, const double (&Ar)[E], unsigned srow, unsigned crow,
                                          double Aj, double Sj, double Cj, const double (&g)[E], const double (&v)[E],
                                          const double (&aux)[E], double (&acc)[3]) {
-  if (op == OP_SE) {            // dK/dv = K / v ; dK/dl = K r^2 / l
+  switch (op) {
+  case OP_SE: {            // dK/dv = K / v ; dK/dl = K r^2 / l
 #pragma unroll
     for (int e = 0; e < E; e++) {
       const double gv = g[e] * v[e];
       acc[0] += gv;
       acc[1] = fma(gv, aux[e], acc[1]);
     }
-  } else if (op == OP_RQ) {     // rational-quadratic.ipynb#2
+  } break;
+  case OP_RQ: {     // rational-quadratic.ipynb#2
     double c1, c3;
     c1 = lds_f64(cst + 8);
     c3 = lds_f64(cst + 24);
@@ -298,7 +306,8 @@ __device__ __forceinline__ void leaf_bwd(int op, unsigned cst, const double (&Ar
       acc[1] = fma(gv, ue, acc[1]);
       acc[2] = fma(gv, ue - aux[e], acc[2]);
     }
-  } else if (op == OP_PER) {    // periodic.ipynb#2
+  } break;
+  case OP_PER: {    // periodic.ipynb#2
     double Sr[E], Cr[E];
     lds_rows<E>(srow, Sr);
     lds_rows<E>(crow, Cr);
@@ -311,15 +320,18 @@ __device__ __forceinline__ void leaf_bwd(int op, unsigned cst, const double (&Ar
       acc[1] = fma(gv * s, c * (Ar[e] - Aj), acc[1]);
       acc[2] = fma(gv * s, s, acc[2]);
     }
-  } else if (op == OP_LIN) {    // linear.ipynb#2
+  } break;
+  case OP_LIN: {    // linear.ipynb#2
 #pragma unroll
     for (int e = 0; e < E; e++) {
       acc[0] = fma(g[e], aux[e], acc[0]);
       acc[1] = fma(g[e], Ar[e] + Aj, acc[1]);
     }
-  } else {
+  } break;
+  default: {
 #pragma unroll
     for (int e = 0; e < E; e++) acc[0] += g[e];
+  } break;
   }
 }
 
