@@ -49,6 +49,8 @@ def _declare(lib):
     lib.b200gp_set_panel_tiles.argtypes = [vp, ctypes.c_int]
     lib.b200gp_set_tile64.restype = ctypes.c_int
     lib.b200gp_set_tile64.argtypes = [vp, ctypes.c_int]
+    lib.b200gp_set_potrf_la.restype = ctypes.c_int
+    lib.b200gp_set_potrf_la.argtypes = [vp, ctypes.c_int]
     lib.b200gp_set_tma.restype = ctypes.c_int
     lib.b200gp_set_tma.argtypes = [vp, ctypes.c_int]
     lib.b200gp_set_fused_grad.restype = ctypes.c_int
@@ -94,7 +96,7 @@ def _declare(lib):
     lib.b200gp_alignment_min_slots.argtypes = [ctypes.c_int, ctypes.c_int]
 
 EXPORTS = ['b200gp_version', 'b200gp_create', 'b200gp_destroy', 'b200gp_last_error', 'b200gp_set_quirks', 'b200gp_set_lookup',
-           'b200gp_set_profiling', 'b200gp_set_panel_tiles', 'b200gp_set_fused_grad', 'b200gp_set_tile64', 'b200gp_set_tma', 'b200gp_launch_count', 'b200gp_last_phase_ms', 'b200gp_workspace_bytes',
+           'b200gp_set_profiling', 'b200gp_set_panel_tiles', 'b200gp_set_fused_grad', 'b200gp_set_tile64', 'b200gp_set_potrf_la', 'b200gp_set_tma', 'b200gp_launch_count', 'b200gp_last_phase_ms', 'b200gp_workspace_bytes',
            'b200gp_bind', 'b200gp_build_K', 'b200gp_lml_grad', 'b200gp_posterior', 'b200gp_potrf_work_bytes', 'b200gp_potrf',
            'b200gp_hellinger_precompute', 'b200gp_hellinger_pairs_work_bytes', 'b200gp_hellinger_pairs', 'b200gp_gram_logdet', 'b200gp_hellinger_pairs_large_work_bytes',
            'b200gp_hellinger_pairs_large', 'b200gp_vector_pairs', 'b200gp_centered_alignments', 'b200gp_alignment_min_slots']

@@ -49,6 +49,7 @@ struct b200gp_ctx {
   bool panel_user = false;      // b200gp_set_panel_tiles was called: no adaptive choice
   int batch_panel_tiles = 8;    // batched Cholesky / L^-T (measured: 4 -> 26.6, 8 -> 26.2 ms per 256 items at N = 2048)
   int gemm64 = 1;               // Cholesky / L^-T updates on 64 x 64 CTA tiles
+  int potrf_la = 1;             // diagonal tiles by the look-ahead register factorisation
   bool kinv64 = true;           // K^-1 on 64 x 64 CTA tiles with CTA-granular skipping (kinv64_kernel) instead of kinv_kernel
   bool fused_grad = false;      // K^-1 and the gradient of the <= 4-leaf programs in one kernel (kinv_grad_kernel)
   int tma = 3;                  // 64 x 64 tile GEMMs fed by the TMA (1 + swizzle mode, tile_gemm64_tma.cuh); 0: cp.async
@@ -227,6 +228,13 @@ int b200gp_set_tile64(b200gp_ctx* c, int enabled) {
   return 0;
 }
 
+int b200gp_set_potrf_la(b200gp_ctx* c, int enabled) {
+  if (!c) return -1;
+  c->potrf_la = enabled ? 1 : 0;
+  c->base.potrf_la = c->potrf_la;
+  return 0;
+}
+
 static void encode_bound_maps(b200gp_ctx* c) {
   c->tma_ok = false;
   c->base.tma = 0;
@@ -293,6 +301,7 @@ int b200gp_bind(b200gp_ctx* c, void* ws, size_t ws_bytes, int slots, int max_par
   b.logdet_part = l.logdet_part; b.diag_part = l.diag_part; b.grad_part = l.grad_part; b.solve_part = l.solve_part;
   b.pstride = max_params + 1;
   b.gemm64 = c->gemm64;
+  b.potrf_la = c->potrf_la;
   b.slot_status = l.slot_status;
   b.Xt = l.Xt; b.y = l.y;
   b.cprog = l.cprog; b.klist = l.klist; b.kcount = l.kcount; b.list_stride = slots;
@@ -655,6 +664,7 @@ int b200gp_potrf(b200gp_ctx* c, double* dA, int N, void* work, double* logdet, i
   b.N = N; b.Np = N; b.T = T; b.D = 0; b.nslots = 1; b.mstride = (size_t)N * N;
   b.M1 = dA; b.M2 = nullptr;
   b.gemm64 = c->gemm64;
+  b.potrf_la = c->potrf_la;
   if (c->tma != 0 && tma_maps_bytes() <= sizeof c->tmaps_potrf &&
       tma_encode_maps(c->tmaps_potrf, dA, nullptr, N, (size_t)N, (c->tma == 4 ? 3 : c->tma) - 1) == 0) {
     b.tma = c->tma;

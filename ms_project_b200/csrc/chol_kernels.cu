@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 #include "gemm_body.cuh"
 #include "tile_gemm64.cuh"
+#include "tile_potrf_la.cuh"
 #include "tile_gemm64_tma.cuh"
 #include "tile_potrf_blocked.cuh"
 
@@ -88,8 +89,55 @@ __global__ void __launch_bounds__(TB_THREADS, 1) potrf_diag_kernel(Batch b, int 
     }
 }
 
+// The same step on the look-ahead factorisation of [A | I] (tile_potrf_la.cuh): L, D = L^-1 and V_kk = D^T go from the
+// registers straight to global memory (a warp covers 8 rows x 32 bytes of L and of V, 4 rows x 64 bytes of D).
+__global__ void __launch_bounds__(TL_THREADS, 1) potrf_diag_la_kernel(Batch b, int k) {
+  const int slot = b.slot0 + blockIdx.x;
+  if (b.slot_status[slot] != 0) return;
+  __shared__ TileLaSmem S;
+  int ty, tx;
+  tile_la_coords(ty, tx);
+  double* A = b.M1 + slot * b.mstride + (size_t)(k * NB) * b.Np + k * NB;
+  double a[TL_NE], w[TL_NE];
+#pragma unroll
+  for (int p = 0; p < TL_R; p++)
+#pragma unroll
+    for (int q = 0; q <= p; q++) a[tl_idx(p, q)] = A[(size_t)(ty + 16 * p) * b.Np + tx + 16 * q];
+  tile_potrf_inverse_la(a, w, S);
+  if (S.fail != 0) {   // uniform
+    if (threadIdx.x == 0) b.slot_status[slot] = k * NB + S.fail;
+    return;
+  }
+  if (threadIdx.x < 32) {      // log-determinant partial, reduced in a fixed order
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < NB / 32; r++) s += log(S.piv[threadIdx.x + 32 * r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) b.logdet_part[slot * b.T + k] = s;
+  }
+  double* Dk = b.Dinv + ((size_t)slot * b.T + k) * (NB * NB);
+  double* V = b.M2 ? b.M2 + slot * b.mstride + (size_t)(k * NB) * b.Np + k * NB : nullptr;
+#pragma unroll
+  for (int p = 0; p < TL_R; p++)
+#pragma unroll
+    for (int q = 0; q < TL_R; q++) {
+      {   // L: element (ty + 16 p, tx + 16 q); the strict upper part of the tile is zeroed
+        const int i = ty + 16 * p, c = tx + 16 * q;
+        A[(size_t)i * b.Np + c] = (q <= p && c <= i) ? a[tl_idx(q <= p ? p : 0, q <= p ? q : 0)] : 0.0;
+      }
+      {   // D: element (tx + 16 p, ty + 16 q), exact zeros above the diagonal; V_kk = D^T
+        const int i = tx + 16 * p, c = ty + 16 * q;
+        const double v = (q <= p) ? w[tl_idx(q <= p ? p : 0, q <= p ? q : 0)] : 0.0;
+        Dk[i * NB + c] = v;
+        if (V) V[(size_t)c * b.Np + i] = v;
+      }
+    }
+}
+
 void launch_potrf_diag(const Batch& b, int k, cudaStream_t s) {
-  potrf_diag_kernel<<<b.nslots, TB_THREADS, PD_SMEM_BYTES, s>>>(b, k);
+  if (b.potrf_la) potrf_diag_la_kernel<<<b.nslots, TL_THREADS, 0, s>>>(b, k);
+  else potrf_diag_kernel<<<b.nslots, TB_THREADS, PD_SMEM_BYTES, s>>>(b, k);
   g_launch_count++;
 }
 

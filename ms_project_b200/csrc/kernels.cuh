@@ -46,6 +46,7 @@ struct Batch {
   const double* lut;         // OP_LOOKUP distance matrix (lut_n x lut_n, b200gp_set_lookup) or null
   int lut_n;
   int gemm64;                // 1: Cholesky / L^-T updates on 64 x 64 CTA tiles (chol_update64 / inv_update64), 0: 128 x 64 tiles
+  int potrf_la;              // 1: diagonal tiles by the look-ahead register factorisation (tile_potrf_la.cuh), 0: the blocked one
   int tma;                   // 0: the 64 x 64 tile GEMMs stage their operands with cp.async; 1 + SW: with the TMA (tile_gemm64_tma.cuh)
                              // and swizzle mode SW (0 none, 1 128B, 2 128B_ATOM_32B) of the tensor maps below
   const void* tmaps;         // host pointer: TmaMaps of this batch's M1 / M2 (launch-time only; kernels get the maps by value)

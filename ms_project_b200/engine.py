@@ -73,6 +73,10 @@ class Engine(object):
         """CTA tile shape of the DMMA phases: 64 x 64 (default) or 128 x 64; bit-identical results."""
         _lib.check(self.ctx, self.lib.b200gp_set_tile64(self.ctx, int(bool(on))), 'b200gp_set_tile64')
 
+    def set_potrf_la(self, on):
+        """Diagonal tiles by the look-ahead register factorisation (default) or the blocked one; same results up to rounding."""
+        _lib.check(self.ctx, self.lib.b200gp_set_potrf_la(self.ctx, int(bool(on))), 'b200gp_set_potrf_la')
+
     def set_tma(self, mode):
         """Operand staging of the 64 x 64 tile GEMMs: 3 TMA + 32-byte-atom swizzle (default), 2 TMA + 128-byte swizzle,
         1 TMA unswizzled, 0 cp.async; bit-identical results."""

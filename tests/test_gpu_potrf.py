@@ -14,8 +14,16 @@ def spd(n, seed, cond_boost=1e-3):
     return np.exp(-0.5 * d * d / 0.6 ** 2) + np.cos(0.3 * d) * 0.2 + (0.2 + cond_boost) * np.eye(n)
 
 
+@pytest.fixture(params=[1, 0], ids=['lookahead', 'blocked'])
+def diag_mode(engine, request):
+    """Both diagonal-tile factorisations (b200gp_set_potrf_la): look-ahead [A | I] elimination (default) and blocked."""
+    engine.set_potrf_la(request.param)
+    yield request.param
+    engine.set_potrf_la(1)
+
+
 @pytest.mark.parametrize('n', [128, 256, 640, 2048])
-def test_potrf_matches_lapack(engine, n):
+def test_potrf_matches_lapack(engine, n, diag_mode):
     import torch
     K = spd(n, n)
     A = torch.from_numpy(K.copy()).to(engine.device)
@@ -28,7 +36,7 @@ def test_potrf_matches_lapack(engine, n):
     assert np.max(np.abs(L @ L.T - K)) <= 1e-12 * n
 
 
-def test_potrf_reports_first_bad_pivot(engine):
+def test_potrf_reports_first_bad_pivot(engine, diag_mode):
     import torch
     n = 256
     K = spd(n, 3)
