@@ -387,46 +387,18 @@ __device__ __forceinline__ void poly_prologue(PolySmem<LMAX>& S, const Batch& b,
   }
 }
 
-// p[e] = product of the leaf values selected by the slot mask `m` (1 for the empty mask).  With 4 slots the 16 masks are a
-// jump table of straight-line products -- exactly the multiplications the term needs; the generic form multiplies through
-// per-bit selects (p *= bit ? v : 1), which cost two FSELs and a wasted DMUL per absent leaf.
+// p[e] = product of the leaf values selected by the slot mask `m` (1 for the empty mask): the term loop of the 5-8 leaf
+// kernels (the <= 4-leaf kernels evaluate their polynomial by canonical shape, below).
 template <int LMAX, int E>
 __device__ __forceinline__ void mask_product(const double (&v)[LMAX][E], unsigned m, double (&p)[E]) {
-  if (LMAX == 4) {
-#define MP1(a) for (int e = 0; e < E; e++) p[e] = v[a][e]; break
-#define MP2(a, b) for (int e = 0; e < E; e++) p[e] = v[a][e] * v[b][e]; break
-#define MP3(a, b, c) for (int e = 0; e < E; e++) p[e] = v[a][e] * v[b][e] * v[c][e]; break
-    switch (m & 15u) {
-      case 0: for (int e = 0; e < E; e++) p[e] = 1.0; break;
-      case 1: MP1(0);
-      case 2: MP1(1);
-      case 4: MP1(2);
-      case 8: MP1(3);
-      case 3: MP2(0, 1);
-      case 5: MP2(0, 2);
-      case 9: MP2(0, 3);
-      case 6: MP2(1, 2);
-      case 10: MP2(1, 3);
-      case 12: MP2(2, 3);
-      case 7: MP3(0, 1, 2);
-      case 11: MP3(0, 1, 3);
-      case 13: MP3(0, 2, 3);
-      case 14: MP3(1, 2, 3);
-      default: for (int e = 0; e < E; e++) p[e] = (v[0][e] * v[1][e]) * (v[2][e] * v[3][e]); break;
+#pragma unroll
+  for (int e = 0; e < E; e++) p[e] = 1.0;
+#pragma unroll
+  for (int l = 0; l < LMAX; l++)
+    if (m & (1u << l)) {
+#pragma unroll
+      for (int e = 0; e < E; e++) p[e] *= v[l][e];
     }
-#undef MP1
-#undef MP2
-#undef MP3
-  } else {
-#pragma unroll
-    for (int e = 0; e < E; e++) p[e] = 1.0;
-#pragma unroll
-    for (int l = 0; l < LMAX; l++)
-      if (m & (1u << l)) {
-#pragma unroll
-        for (int e = 0; e < E; e++) p[e] *= v[l][e];
-      }
-  }
 }
 
 // K and the adjoints dK/dv_l of the canonical <= 4-leaf shapes (cprog.cuh), in factored form: one switch per row step.
@@ -478,10 +450,8 @@ __device__ __forceinline__ void shape_adjoints(int shape, const double (&v)[4][E
 }
 #undef SH_ALL
 
-// product-term masks: 4 leaf slots expand to at most 4 terms (one register); 8 slots read shared memory
-template <int LMAX>
-__device__ __forceinline__ unsigned term_mask(unsigned terms4, unsigned term_addr, int g) {
-  if (LMAX == 4) return (terms4 >> (8 * g)) & 0xffu;
+// product-term mask g of the slot's program (5-8 leaf kernels): a byte of the CProg copy in shared memory
+__device__ __forceinline__ unsigned term_mask(unsigned term_addr, int g) {
   unsigned m;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(m) : "r"(term_addr + g));
   return m;
@@ -507,7 +477,6 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? POLY_BUILD_CTAS : 2) poly_bui
     poly_prologue<LMAX>(S, b, slot, ti, tj, c, Aj, Sj, Cj, ops);
     __syncthreads();
     const int L = S.cp.L, G = S.cp.G, shape = S.cp.shape;
-    const unsigned terms4 = *reinterpret_cast<const unsigned*>(S.cp.term);
     const double diag_add = b.add_diag == 1 ? S.noise + EXACT_INFERENCE_JITTER + (b.jitter ? b.jitter[slot] : 0.0)
                                              : (b.add_diag == 2 ? S.noise : 0.0);
     double* out = b.M1 + slot * b.mstride + (size_t)(ti * NB) * b.Np + tj * NB + c;
@@ -534,7 +503,7 @@ __global__ void __launch_bounds__(256, LMAX == 4 ? POLY_BUILD_CTAS : 2) poly_bui
 #pragma unroll
         for (int e = 0; e < E; e++) k[e] = 0.0;
         for (int g = 0; g < G; g++) {
-          const unsigned mask = term_mask<LMAX>(terms4, sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), g);
+          const unsigned mask = term_mask(sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), g);
           double p[E];
           mask_product<LMAX, E>(v, mask, p);
 #pragma unroll
@@ -591,7 +560,6 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
   const double aj = b.alpha[(size_t)slot * b.Np + tj * NB + col0 + c];
   __syncthreads();
   const int L = S.cp.L, G = S.cp.G, single = S.cp.single, shape = S.cp.shape;
-  const unsigned terms4 = *reinterpret_cast<const unsigned*>(S.cp.term);
   double acc[LMAX][3], accn = 0.0;
 #pragma unroll
   for (int l = 0; l < LMAX; l++) { acc[l][0] = 0.0; acc[l][1] = 0.0; acc[l][2] = 0.0; }
@@ -656,7 +624,7 @@ __device__ __forceinline__ void poly_grad_tile(PolySmem<LMAX>& S, unsigned sb, c
           for (int e = 0; e < E; e++) adj[e] = 0.0;
           {
             for (int t = 0; t < G; t++) {
-              const unsigned mask = term_mask<LMAX>(terms4, sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), t);
+              const unsigned mask = term_mask(sb + (unsigned)offsetof(SM, cp) + (unsigned)offsetof(CProg, term), t);
               if (!(mask & (1u << l))) continue;
               double p[E];
               mask_product<LMAX, E>(v, mask & ~(1u << l), p);
