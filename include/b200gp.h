@@ -170,9 +170,11 @@ int b200gp_set_panel_tiles(b200gp_ctx* ctx, int tiles);
  * (tests/test_gpu_fullsize.py); the 64 x 64 form is 3-5 % faster on every phase. */
 int b200gp_set_tile64(b200gp_ctx* ctx, int enabled);
 /* Diagonal 128 x 128 tiles (Cholesky factor + triangular inverse, the latency-critical step of every blocked phase).
- * 1 (default): look-ahead register factorisation of [A | I], one column per barrier (csrc/tile_potrf_la.cuh); 0: blocked
- * over 16-column panels (csrc/tile_potrf_blocked.cuh).  Same results up to rounding (tests/test_gpu_potrf.py runs both). */
-int b200gp_set_potrf_la(b200gp_ctx* ctx, int enabled);
+ * 1 (default): look-ahead register factorisation of [A | I], one column per block barrier (csrc/tile_potrf_la.cuh); 2: the
+ * same with a split barrier (mbarrier arrive after the early publish, wait at the next step: bit-identical, measured 0.7 %
+ * faster on a lone evaluation); 0: blocked over 16-column panels (csrc/tile_potrf_blocked.cuh).  Same results up to rounding
+ * between 0 and 1 / 2 (tests/test_gpu_potrf.py runs all three). */
+int b200gp_set_potrf_la(b200gp_ctx* ctx, int mode);
 /* How the 64 x 64 tile GEMMs stage their operands.  3 (default): TMA (`cp.async.bulk.tensor.2d` into an mbarrier-guarded
  * ring, csrc/tile_gemm64_tma.cuh) with tensor maps swizzled SWIZZLE_128B_ATOM_32B; 2: TMA, SWIZZLE_128B; 1: TMA, no swizzle;
  * 0: cp.async (LDGSTS) with a block barrier per K chunk; 4: as 3 with a 3-stage ring and four CTAs per SM (measured equal).

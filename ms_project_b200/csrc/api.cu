@@ -230,7 +230,7 @@ int b200gp_set_tile64(b200gp_ctx* c, int enabled) {
 
 int b200gp_set_potrf_la(b200gp_ctx* c, int enabled) {
   if (!c) return -1;
-  c->potrf_la = enabled ? 1 : 0;
+  c->potrf_la = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);
   c->base.potrf_la = c->potrf_la;
   return 0;
 }

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) potrf_diag_kernel(Batch b, int 
 
 // The same step on the look-ahead factorisation of [A | I] (tile_potrf_la.cuh): L, D = L^-1 and V_kk = D^T go from the
 // registers straight to global memory (a warp covers 8 rows x 32 bytes of L and of V, 4 rows x 64 bytes of D).
+template <bool SPLIT>
 __global__ void __launch_bounds__(TL_THREADS, 1) potrf_diag_la_kernel(Batch b, int k) {
   const int slot = b.slot0 + blockIdx.x;
   if (b.slot_status[slot] != 0) return;
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) potrf_diag_la_kernel(Batch b, i
   for (int p = 0; p < TL_R; p++)
 #pragma unroll
     for (int q = 0; q <= p; q++) a[tl_idx(p, q)] = A[(size_t)(ty + 16 * p) * b.Np + tx + 16 * q];
-  tile_potrf_inverse_la(a, w, S);
+  tile_potrf_inverse_la<SPLIT>(a, w, S);
   if (S.fail != 0) {   // uniform
     if (threadIdx.x == 0) b.slot_status[slot] = k * NB + S.fail;
     return;
@@ -136,7 +137,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) potrf_diag_la_kernel(Batch b, i
 }
 
 void launch_potrf_diag(const Batch& b, int k, cudaStream_t s) {
-  if (b.potrf_la) potrf_diag_la_kernel<<<b.nslots, TL_THREADS, 0, s>>>(b, k);
+  if (b.potrf_la == 2) potrf_diag_la_kernel<true><<<b.nslots, TL_THREADS, 0, s>>>(b, k);
+  else if (b.potrf_la) potrf_diag_la_kernel<false><<<b.nslots, TL_THREADS, 0, s>>>(b, k);
   else potrf_diag_kernel<<<b.nslots, TB_THREADS, PD_SMEM_BYTES, s>>>(b, k);
   g_launch_count++;
 }

@@ -40,8 +40,25 @@ struct TileLaSmem {
   double wrow[2][NB];     // [step parity][column c]: row j of W when step j starts (exact zeros for c > j)
   double inv[2];          // [step parity]: 1 / d_j
   double piv[NB];         // pivots d_j
+  unsigned long long bar; // split barrier (mbarrier): a thread arrives once it has published, waits when it needs the next operands
   int fail;               // 1-based index of the first non-positive / non-finite pivot (0 = none)
 };
+
+__device__ __forceinline__ void tl_bar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tl_bar_arrive(unsigned bar) {       // release: this thread's loads and stores so far come first
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tl_bar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TL_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra TL_WAIT;\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
 
 __host__ __device__ constexpr int tl_idx(int p, int q) { return p * (p + 1) / 2 + q; }    // block (p, q), q <= p
 
@@ -72,12 +89,17 @@ __device__ __forceinline__ double tl_rsqrt(double d) {
 }
 
 // One elimination step: column j = 16 JB + jj, PAR = j & 1, LAST = (jj == 15).
-template <int JB, bool LAST, int PAR>
+template <int JB, bool LAST, int PAR, bool SPLIT>
 __device__ __forceinline__ void tile_la_step(double (&a)[TL_NE], double (&w)[TL_NE], TileLaSmem& S, int jj, int ty, int tx) {
   constexpr int QN = LAST ? JB + 1 : JB;       // block column of column j + 1 = block row of row j + 1 of W
   const double* cA = S.col[PAR];
   const double* wA = S.wrow[PAR];
-  __syncthreads();
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&S.bar);
+  // SPLIT: phase j of the barrier completes when every thread has arrived after its step j - 1 publish (all of them arrive,
+  // owners or not) -- by the time a thread gets here the others usually have, so warps drift apart by up to a step
+  // instead of meeting 128 times
+  if (SPLIT) tl_bar_wait(bar, PAR);           // phase j has parity j & 1
+  else __syncthreads();
   const double i0 = S.inv[PAR];
   // operands: multipliers of the rows ty + 16 p (A) and tx + 16 p (W), column values of the columns tx + 16 q, row j of W
   double r0[TL_R], cq[TL_R], wr[TL_R];
@@ -109,6 +131,14 @@ __device__ __forceinline__ void tile_la_step(double (&a)[TL_NE], double (&w)[TL_
     }
   }
   const double inv_next = (QN < TL_R) ? tl_rcp(a[tl_idx(QN < TL_R ? QN : 0, QN < TL_R ? QN : 0)]) : 0.0;
+  if (SPLIT && QN < TL_R) {
+    // the pivot's owner waits for its reciprocal here (one warp, ~60 cycles); everybody arrives and goes on
+    if (tx == txn && ty == txn) {
+      S.inv[PAR ^ 1] = inv_next;
+      S.piv[JB * 16 + 1 + jj] = a[tl_idx(QN < TL_R ? QN : 0, QN < TL_R ? QN : 0)];
+    }
+    tl_bar_arrive(bar);
+  }
   // the rest of the trailing update of A ...
 #pragma unroll
   for (int q = JB; q < TL_R; q++) {
@@ -126,7 +156,7 @@ __device__ __forceinline__ void tile_la_step(double (&a)[TL_NE], double (&w)[TL_
 #pragma unroll
     for (int q = 0; q <= JB; q++) w[tl_idx(p, q)] = fma(-mw, wr[q], w[tl_idx(p, q)]);
   }
-  if (QN < TL_R) {
+  if (!SPLIT && QN < TL_R) {                   // (the reciprocal's chain has run under the multiply-adds above)
     if (tx == txn && ty == txn) {
       S.inv[PAR ^ 1] = inv_next;
       S.piv[JB * 16 + 1 + jj] = a[tl_idx(QN < TL_R ? QN : 0, QN < TL_R ? QN : 0)];
@@ -134,21 +164,21 @@ __device__ __forceinline__ void tile_la_step(double (&a)[TL_NE], double (&w)[TL_
   }
 }
 
-template <int JB>
+template <int JB, bool SPLIT>
 struct TileLaBlocks {
   static __device__ __forceinline__ void run(double (&a)[TL_NE], double (&w)[TL_NE], TileLaSmem& S, int ty, int tx) {
 #pragma unroll 1
     for (int jj = 0; jj < 14; jj += 2) {
-      tile_la_step<JB, false, 0>(a, w, S, jj, ty, tx);
-      tile_la_step<JB, false, 1>(a, w, S, jj + 1, ty, tx);
+      tile_la_step<JB, false, 0, SPLIT>(a, w, S, jj, ty, tx);
+      tile_la_step<JB, false, 1, SPLIT>(a, w, S, jj + 1, ty, tx);
     }
-    tile_la_step<JB, false, 0>(a, w, S, 14, ty, tx);
-    tile_la_step<JB, true, 1>(a, w, S, 15, ty, tx);
-    TileLaBlocks<JB + 1>::run(a, w, S, ty, tx);
+    tile_la_step<JB, false, 0, SPLIT>(a, w, S, 14, ty, tx);
+    tile_la_step<JB, true, 1, SPLIT>(a, w, S, 15, ty, tx);
+    TileLaBlocks<JB + 1, SPLIT>::run(a, w, S, ty, tx);
   }
 };
-template <>
-struct TileLaBlocks<TL_R> {
+template <bool SPLIT>
+struct TileLaBlocks<TL_R, SPLIT> {
   static __device__ __forceinline__ void run(double (&)[TL_NE], double (&)[TL_NE], TileLaSmem&, int, int) {}
 };
 
@@ -156,9 +186,14 @@ struct TileLaBlocks<TL_R> {
 // On exit:  a = L in the same layout (entries above the diagonal inside the diagonal blocks are junk: the caller masks
 // them), w[tl_idx(p, q)] = D(tx + 16 p, ty + 16 q) with D = L^-1 (exact zeros above the diagonal), S.piv = the pivots,
 // S.fail = first bad pivot (then a and w are meaningless).
+template <bool SPLIT>
 __device__ __forceinline__ void tile_potrf_inverse_la(double (&a)[TL_NE], double (&w)[TL_NE], TileLaSmem& S) {
   int ty, tx;
   tile_la_coords(ty, tx);
+  if (SPLIT) {
+    if (threadIdx.x == 0) tl_bar_init((unsigned)__cvta_generic_to_shared(&S.bar), TL_THREADS);
+    __syncthreads();
+  }
 #pragma unroll
   for (int p = 0; p < TL_R; p++)
 #pragma unroll
@@ -169,7 +204,8 @@ __device__ __forceinline__ void tile_potrf_inverse_la(double (&a)[TL_NE], double
     S.wrow[0][ty] = (ty == 0) ? 1.0 : 0.0;     // row 0 of W = e_0 (block column 0 only: step 0 reads nothing else)
     if (ty == 0) { S.inv[0] = tl_rcp(a[0]); S.piv[0] = a[0]; }
   }
-  TileLaBlocks<0>::run(a, w, S, ty, tx);
+  if (SPLIT) tl_bar_arrive((unsigned)__cvta_generic_to_shared(&S.bar));      // phase 0: column 0, row 0 of W, 1 / d_0 are published
+  TileLaBlocks<0, SPLIT>::run(a, w, S, ty, tx);
   __syncthreads();
   // first bad pivot (a bad pivot poisons the later ones, the earlier ones are good by definition)
   if (threadIdx.x < 32) {

@@ -74,8 +74,9 @@ class Engine(object):
         _lib.check(self.ctx, self.lib.b200gp_set_tile64(self.ctx, int(bool(on))), 'b200gp_set_tile64')
 
     def set_potrf_la(self, on):
-        """Diagonal tiles by the look-ahead register factorisation (default) or the blocked one; same results up to rounding."""
-        _lib.check(self.ctx, self.lib.b200gp_set_potrf_la(self.ctx, int(bool(on))), 'b200gp_set_potrf_la')
+        """Diagonal tiles: 1 look-ahead register factorisation (default), 2 the same with a split barrier (bit-identical),
+        0 the blocked one (same results up to rounding)."""
+        _lib.check(self.ctx, self.lib.b200gp_set_potrf_la(self.ctx, int(on)), 'b200gp_set_potrf_la')
 
     def set_tma(self, mode):
         """Operand staging of the 64 x 64 tile GEMMs: 3 TMA + 32-byte-atom swizzle (default), 2 TMA + 128-byte swizzle,

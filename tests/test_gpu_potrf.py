@@ -14,7 +14,7 @@ def spd(n, seed, cond_boost=1e-3):
     return np.exp(-0.5 * d * d / 0.6 ** 2) + np.cos(0.3 * d) * 0.2 + (0.2 + cond_boost) * np.eye(n)
 
 
-@pytest.fixture(params=[1, 0], ids=['lookahead', 'blocked'])
+@pytest.fixture(params=[1, 2, 0], ids=['lookahead', 'lookahead-split-barrier', 'blocked'])
 def diag_mode(engine, request):
     """Both diagonal-tile factorisations (b200gp_set_potrf_la): look-ahead [A | I] elimination (default) and blocked."""
     engine.set_potrf_la(request.param)

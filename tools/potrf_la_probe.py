@@ -18,7 +18,7 @@ for N in (512, 2048):
         eng.upload_programs(batch)
         theta = batch.initial_theta(np.full(items, 0.1))
         res = {}
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             eng.set_potrf_la(mode)
             for _ in range(3):
                 lml, g, st, tr = eng.lml_grad(batch, theta)
@@ -29,13 +29,13 @@ for N in (512, 2048):
             torch.cuda.synchronize()
             res[mode] = ((time.perf_counter() - t0) / 20 * 1e3, float(np.sum(lml)), int(np.sum(st != 0)))
         out['N%d_items%d' % (N, items)] = res
-        print(N, items, 'blocked %.3f ms  look-ahead %.3f ms' % (res[0][0], res[1][0]), 'lml rel diff %.2e' % (abs(res[0][1] - res[1][1]) / abs(res[0][1])), res[0][2], res[1][2])
+        print(N, items, 'blocked %.3f ms  look-ahead %.3f ms  split barrier %.3f ms' % (res[0][0], res[1][0], res[2][0]), 'lml rel diff %.2e %.2e' % (abs(res[0][1] - res[1][1]) / abs(res[0][1]), abs(res[2][1] - res[1][1]) / abs(res[1][1])), res[0][2], res[1][2], res[2][2])
 # C5 potrf
 n = 16384
 rng = np.random.default_rng(0)
 x = np.sort(rng.uniform(0, 50, n))
 A0 = torch.from_numpy(np.exp(-0.5 * (x[:, None] - x[None, :]) ** 2) + 0.1 * np.eye(n)).cuda()
-for mode in (0, 1):
+for mode in (0, 1, 2):
     eng.set_potrf_la(mode)
     ts = []
     for r in range(4):
