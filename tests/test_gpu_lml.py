@@ -44,6 +44,50 @@ def test_lml_grad_matches_oracle(engine, n, d):
         assert np.max(np.abs(dlml[a:b] - ref_g)) <= 1e-6 * scale, (KERNELS[i], dlml[a:b], ref_g)
 
 
+# every canonical polynomial shape of the <= 4-leaf kernels (csrc/cprog.cuh), each in two leaf orders / family assignments,
+# so that every case of shape_value / shape_adjoints and the compile kernel's relabelling are exercised
+SHAPES = ['SE_1', 'PER_2',                                                         # 0  a
+          'SE_1 + RQ_2', 'LIN_2 + PER_1',                                          # 1  a + b
+          'SE_1 * PER_2', 'LIN_1 * RQ_1',                                          # 2  ab
+          'SE_1 + RQ_2 + LIN_1', 'PER_2 + LIN_2 + SE_2',                           # 3  a + b + c
+          'SE_1 + RQ_2 * PER_1', 'LIN_1 * SE_2 + PER_2',                           # 4  a + bc
+          'SE_1 * (RQ_2 + PER_1)', '(LIN_2 + SE_1) * RQ_1',                        # 5  a (b + c)
+          'SE_1 * RQ_2 * LIN_1', 'PER_1 * LIN_2 * RQ_2',                           # 6  abc
+          'SE_1 + RQ_2 + PER_1 + LIN_2', 'LIN_1 + PER_2 + RQ_1 + SE_2',            # 7  a + b + c + d
+          'SE_1 + LIN_2 + RQ_1 * PER_2', 'PER_1 * SE_2 + RQ_2 + LIN_1',            # 8  a + b + cd
+          'SE_1 + RQ_2 * (PER_1 + LIN_2)', '(SE_2 + LIN_1) * PER_2 + RQ_1',        # 9  a + b (c + d)
+          'LIN_1 + SE_2 * RQ_1 * PER_2', 'PER_1 * LIN_2 * SE_1 + RQ_2',            # 10 a + bcd
+          'SE_1 * (RQ_2 + PER_1 + LIN_2)', '(LIN_1 + SE_2 + PER_2) * RQ_1',        # 11 a (b + c + d)
+          '(SE_1 + LIN_2) * (RQ_1 + PER_2)', '(PER_1 + RQ_2) * (LIN_1 + SE_2)',    # 12 (a + d)(b + c)
+          'SE_1 * RQ_2 + PER_1 * LIN_2', 'LIN_1 * PER_2 + RQ_1 * SE_2',            # 13 ab + cd
+          'SE_1 * (RQ_2 + PER_1 * LIN_2)', '(LIN_1 * SE_2 + PER_2) * RQ_1',        # 14 a (b + cd)
+          'SE_1 * RQ_2 * (PER_1 + LIN_2)', '(LIN_1 + SE_2) * PER_2 * RQ_1',        # 15 ab (c + d)
+          'SE_1 * RQ_2 * PER_1 * LIN_2', 'LIN_1 * PER_2 * RQ_1 * SE_2']            # 16 abcd
+
+
+def test_every_polynomial_shape_matches_oracle(engine):
+    from ms_project_b200.program import ProgramBatch
+    from oracle import gp
+    X, y = make_data(150, 2, seed=11)                 # two tile rows: diagonal tiles and one below the diagonal
+    kernels = [from_string(s) for s in SHAPES]
+    batch = ProgramBatch(kernels)
+    engine.bind(X, y, slots=len(kernels), max_params=batch.max_params)
+    engine.upload_programs(batch)
+    theta, ks, nz = random_theta(batch, np.random.RandomState(5))
+    lml, dlml, status, tries = engine.lml_grad(batch, theta)
+    K = engine.build_K(batch, theta, add_diag=False)
+    from oracle import kernels as ok
+    for i, k in enumerate(kernels):
+        expr = to_oracle_expr(k)
+        assert np.allclose(K[i], ok.K(expr, ks[i], X), rtol=1e-12, atol=1e-12), SHAPES[i]
+        ref_lml, ref_g, _ = gp.lml_and_grad(expr, ks[i], nz[i], X, y)
+        a, b = batch.theta_off[i], batch.theta_off[i + 1]
+        assert status[i] == 0 and tries[i] == 0
+        assert abs(lml[i] - ref_lml) <= 1e-8 * max(1.0, abs(ref_lml)), (SHAPES[i], lml[i], ref_lml)
+        scale = max(1.0, np.max(np.abs(ref_g)))
+        assert np.max(np.abs(dlml[a:b] - ref_g)) <= 1e-6 * scale, (SHAPES[i], dlml[a:b], ref_g)
+
+
 def test_kernel_matrix_matches_oracle_and_gpml(engine):
     from ms_project_b200.program import ProgramBatch
     from oracle import kernels as ok
