@@ -1,5 +1,6 @@
 """C3 Hellinger pair timing only (500 models, n = 100, 20 samples, 124 750 pairs): `python tools/hp_probe.py [reps]`.
-The pair-kernel variant is chosen by the library (B200GP_HP_VARIANT=0 selects the kernel without look-ahead)."""
+While the pair kernel was being developed the library read B200GP_HP_VARIANT to pick a variant (profiles/experiments/
+hellinger_la_r02.md); the final library dispatches on the subset size only."""
 import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -33,5 +34,5 @@ for _ in range(reps):
     dist, status = builder.pair_distances(ii, jj)
     torch.cuda.synchronize()
     ts.append(time.perf_counter() - t0)
-print(json.dumps({'variant': os.environ.get('B200GP_HP_VARIANT', 'default'), 'precompute_s': t_pre, 'pairs_s': ts,
+print(json.dumps({'precompute_s': t_pre, 'pairs_s': ts,
                   'nan': int(np.isnan(dist).sum()), 'bad': int((status != 0).sum()), 'checksum': float(np.nansum(dist))}))
