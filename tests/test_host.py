@@ -141,3 +141,53 @@ def test_program_limits():
         program.compile_kernel(k)
     with pytest.raises(TypeError):
         program.compile_kernel('SE_1')
+
+
+def test_canonical_shape_table_covers_every_tree_with_up_to_four_leaves():
+    """csrc/cprog.cuh lists the term sets the <= 4-leaf element-wise kernels have straight-line code for.  Every +/* tree over
+    at most four distinct leaves must expand, up to a relabelling of its leaves, to exactly one of them (the compile kernel
+    searches the relabelling; a miss would silently send the program to the slower term-loop kernels)."""
+    import itertools
+    src = open(os.path.join(ROOT, 'ms_project_b200', 'csrc', 'cprog.cuh')).read()
+    body = re.search(r'keys\[CP_NSHAPES\]\s*=\s*\{([^}]*)\}', src).group(1)
+    keys = [int(t, 16) for t in re.findall(r'0x([0-9A-Fa-f]+)', body)]
+    n_shapes = int(re.search(r'constexpr int CP_NSHAPES = (\d+);', src).group(1))
+    assert len(keys) == n_shapes == len(set(keys))
+
+    def leaves_of(s):           # the header's cp_shape_leaves
+        return 1 if s == 0 else (2 if s <= 2 else (3 if s <= 6 else 4))
+
+    def polys(leaves):          # every polynomial (frozenset of term masks) a tree over exactly these leaves expands to
+        if len(leaves) == 1:
+            return {frozenset([1 << leaves[0]])}
+        out = set()
+        for r in range(1, len(leaves)):
+            for sub in itertools.combinations(leaves, r):
+                if leaves[0] not in sub:
+                    continue
+                rest = tuple(x for x in leaves if x not in sub)
+                for a in polys(tuple(sub)):
+                    for b in polys(rest):
+                        out.add(frozenset(a | b))
+                        out.add(frozenset(x | y for x in a for y in b))
+        return out
+
+    def key(masks):
+        k = 0
+        for i, m in enumerate(sorted(masks)):
+            k |= m << (4 * i)
+        return k
+
+    table = {(leaves_of(s), k) for s, k in enumerate(keys)}
+    seen = set()
+    for n in range(1, 5):
+        for p in polys(tuple(range(n))):
+            assert len(p) <= 4
+            hits = set()
+            for perm in itertools.permutations(range(n)):
+                k = key([sum(1 << perm[i] for i in range(n) if m >> i & 1) for m in p])
+                if (n, k) in table:
+                    hits.add(k)
+            assert len(hits) == 1, (n, sorted(p), hits)
+            seen |= {(n, h) for h in hits}
+    assert seen == table          # and no entry of the table is unreachable
