@@ -36,7 +36,8 @@
 #define POLY_E8 1
 #endif
 #ifndef POLY_GE4
-#define POLY_GE4 2             // rows interleaved by the <= 4-leaf gradient kernel (4 would spill at 128 registers)
+#define POLY_GE4 2             // rows interleaved by the <= 4-leaf gradient kernel (4 would spill at 128 registers; 4 rows at one
+                               // CTA per SM, 234 registers: 23.3 instead of 20.1 ms per 768 items)
 #endif
 
 namespace b200gp {
