@@ -5,7 +5,9 @@
 //   precompute:  per (model, sample s)  G_s = K(theta_s) + lambda_s I over the n-point subset, logdet(G_s)
 //   pairs:       per (pair, sample s)   if |ld_i - ld_j| > tol: logdet(1/2 (G_i,s + G_j,s)) else ld_i
 //                                        h_s = 1 - exp(1/4 (ld_i + ld_j) - 1/2 logdet_pq);  d = sqrt(clip(mean_s h_s, 0, 1))
-// Each small factorisation (n <= 128) is one CTA running the in-register Cholesky of tile_potrf.cuh.
+// Each small factorisation (n <= 128) is one CTA running an in-register Cholesky: the precompute kernel the column-at-a-time
+// one of tile_potrf.cuh, the pair kernels (where the time goes: 2.5 million factorisations in C3) the look-ahead forms of
+// tile_potrf_small.cuh -- an 8 x 8 thread grid up to n = 104, a 16 x 8 grid up to 112, a 16 x 16 grid up to 128.
 #include "kernels.cuh"
 #include "kprog.cuh"
 #include "tile_potrf.cuh"
@@ -81,10 +83,10 @@ hellinger_precompute_kernel(const double* __restrict__ Xsub, int n, int D, const
 }
 
 // One CTA per (pair, sample): pivots of chol(1/2 (G_i,s + G_j,s)) by the two-columns-per-barrier register factorisation of
-// tile_potrf_small.cuh.  Only the lower triangle of the two Gram matrices is read; R block rows of 16 cover the order
-// (R = 7 for the 100-point subsets of C3: 28 doubles per thread, three CTAs per SM).  blockIdx.y = sample: every CTA in
-// flight works on the SAME sample, whose M Gram matrices (C3: 500 x 80 KB, half of it touched) stay resident in the
-// 126 MB L2 while all pairs of that sample are processed.
+// tile_potrf_small.cuh on a 16 x 16 thread grid (the form that serves 112 < n <= 128; the look-ahead kernels below serve the
+// smaller orders).  Only the lower triangle of the two Gram matrices is read; R block rows of 16 cover the order.
+// blockIdx.y = sample (all pair kernels): every CTA in flight works on the SAME sample, whose M Gram matrices (C3: 500 x
+// 80 KB, half of it touched) stay resident in the 126 MB L2 while all pairs of that sample are processed.
 template <int R, int MINB, int COLS>
 __global__ void __launch_bounds__(TS_THREADS, MINB)
 hellinger_pair_kernel(const double* __restrict__ logdet, const double* __restrict__ G, int S, int n,
